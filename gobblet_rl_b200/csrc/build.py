@@ -1,0 +1,36 @@
+"""Build libgobblet_b200.so for sm_100a, in-tree (the .so is git-ignored but travels with gpurun)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["gobblet_engine.cu", "gobblet_greedy.cu"]
+HEADERS = ["gobblet_core.cuh", os.path.join("..", "..", "include", "gobblet_b200.h")]
+OUT = os.path.join(HERE, "libgobblet_b200.so")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
+
+
+def stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS + ["build.py"])
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    tmp = OUT + f".tmp{os.getpid()}"
+    cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", tmp, *[os.path.join(HERE, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,403 @@
+// gobblet_core.cuh -- register-resident bitboard engine for 3x3 Gobblet Gobblers (sm_100a).
+//
+// One environment per thread.  The per-env state is kept MOVER-RELATIVE:
+//   xo, yo : 27-bit boards of the mover's odd / even pieces (pieces 1,3,5 / 2,4,6), bit 9*level+pos
+//            -- the reference's `squares` index (gobblet_rl/game/board.py:33, :76-79)
+//   xp, yp : same for the opponent
+//   s[4]   : the 117-bit observation bitmap the mover would see, bit pos*13+c  (gobblet.py:188-208)
+// Everything below is integer bit arithmetic; nothing is a contraction, so no tensor cores.
+#pragma once
+#include <stdint.h>
+
+namespace gbl {
+
+constexpr uint32_t F0 = 0x000001FFu, F1 = 0x0003FE00u, F2 = 0x07FC0000u, B27 = 0x07FFFFFFu;
+
+// ---- 128-bit constants of the observation bitmap -------------------------------------------
+constexpr uint32_t obs_mask_word(int word, int c_lo, int c_hi) {
+    uint32_t m = 0;
+    for (int p = 0; p < 9; ++p)
+        for (int c = c_lo; c <= c_hi; ++c) {
+            int b = 13 * p + c;
+            if ((b >> 5) == word) m |= 1u << (b & 31);
+        }
+    return m;
+}
+constexpr uint32_t OWN_0 = obs_mask_word(0, 0, 5), OWN_1 = obs_mask_word(1, 0, 5), OWN_2 = obs_mask_word(2, 0, 5), OWN_3 = obs_mask_word(3, 0, 5);
+constexpr uint32_t OPP_0 = obs_mask_word(0, 6, 11), OPP_1 = obs_mask_word(1, 6, 11), OPP_2 = obs_mask_word(2, 6, 11), OPP_3 = obs_mask_word(3, 6, 11);
+constexpr uint32_t P12_0 = obs_mask_word(0, 12, 12), P12_1 = obs_mask_word(1, 12, 12), P12_2 = obs_mask_word(2, 12, 12), P12_3 = obs_mask_word(3, 12, 12);
+
+// PTX shifts clamp the amount at 32 (result 0), unlike C++ where >= 32 is undefined.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+#else  // host-side emulation used only by tests/emul (never by the product)
+    return s >= 32u ? 0u : v << s;
+#endif
+}
+
+struct Env {
+    uint32_t xo, yo, xp, yp;  // mover-relative boards
+    uint32_t s[4];            // mover-relative observation bitmap
+    uint32_t agent;           // agent_selection: 0 = player_1 (gobblet.py:160-161)
+    uint32_t plies;           // raw_env.turn (gobblet.py:270)
+    uint32_t done, trunc;     // terminations / truncations (gobblet.py:263; wrapper :114)
+};
+
+struct Stats {
+    uint32_t episodes, p1w, p2w, steps, sumlen, illegal, both, maxlen;
+};
+
+__device__ __forceinline__ void env_clear(Env &e) {  // raw_env.reset, gobblet.py:275-290
+    e.xo = e.yo = e.xp = e.yp = 0;
+    e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0;
+    e.agent = 0; e.plies = 0; e.done = 0; e.trunc = 0;
+}
+
+// set bit b of the 117-bit bitmap; negative b is a no-op (clamped shifts)
+__device__ __forceinline__ void s_or_bit(uint32_t (&s)[4], int b) {
+    uint32_t ub = (uint32_t)b;
+    s[0] |= shl_clamp(1u, ub);
+    s[1] |= shl_clamp(1u, ub - 32u);
+    s[2] |= shl_clamp(1u, ub - 64u);
+    s[3] |= shl_clamp(1u, ub - 96u);
+}
+
+// observation bitmap from the boards: plane c (piece c+1) of the mover at 0..5, opponent 6..11,
+// plane 12 = mover is player_2 (gobblet.py:188-206)
+__device__ __forceinline__ void rebuild_obs_bits(Env &e) {
+    e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0;
+    const uint32_t w[4] = {e.xo, e.yo, e.xp, e.yp};
+    const int cbase[4] = {0, 1, 6, 7};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            uint32_t field = (w[i] >> (9 * f)) & 0x1FFu;
+            int pos = __ffs(field) - 1;  // -1 when the piece is not on the board
+            s_or_bit(e.s, 13 * pos + cbase[i] + 2 * f);
+        }
+    if (e.agent) { e.s[0] |= P12_0; e.s[1] |= P12_1; e.s[2] |= P12_2; e.s[3] |= P12_3; }
+}
+
+// ---- HBM state (16 B / env, absolute player_1 / player_2 layout, see include/gobblet_b200.h) ----
+__device__ __forceinline__ void env_unpack(Env &e, ulonglong2 v) {
+    uint32_t x1 = (uint32_t)v.x & B27, y1 = (uint32_t)(v.x >> 27) & B27;
+    uint32_t x2 = (uint32_t)v.y & B27, y2 = (uint32_t)(v.y >> 27) & B27;
+    uint32_t meta = (uint32_t)(v.x >> 54) | ((uint32_t)(v.y >> 54) << 10);
+    e.agent = meta & 1u; e.done = (meta >> 1) & 1u; e.trunc = (meta >> 2) & 1u; e.plies = meta >> 3;
+    if (e.agent == 0) { e.xo = x1; e.yo = y1; e.xp = x2; e.yp = y2; }
+    else              { e.xo = x2; e.yo = y2; e.xp = x1; e.yp = y1; }
+    rebuild_obs_bits(e);
+}
+
+__device__ __forceinline__ ulonglong2 env_pack(const Env &e) {
+    uint32_t x1, y1, x2, y2;
+    if (e.agent == 0) { x1 = e.xo; y1 = e.yo; x2 = e.xp; y2 = e.yp; }
+    else              { x1 = e.xp; y1 = e.yp; x2 = e.xo; y2 = e.yo; }
+    uint32_t plies = e.plies > 0x1FFFFu ? 0x1FFFFu : e.plies;
+    uint32_t meta = e.agent | (e.done << 1) | (e.trunc << 2) | (plies << 3);
+    ulonglong2 v;
+    v.x = (uint64_t)x1 | ((uint64_t)y1 << 27) | ((uint64_t)(meta & 0x3FFu) << 54);
+    v.y = (uint64_t)x2 | ((uint64_t)y2 << 27) | ((uint64_t)(meta >> 10) << 54);
+    return v;
+}
+
+// ---- rules -------------------------------------------------------------------------------------
+// Occupancy summary shared by legality and the winner test.
+//   u  field s = squares holding a piece of size >= s      (gobble rule, board.py:106-115)
+//   up field s = squares holding a piece of size  > s      (check_covered, board.py:203-220)
+__device__ __forceinline__ void occupancy(const Env &e, uint32_t &u, uint32_t &up) {
+    uint32_t occ = e.xo | e.yo | e.xp | e.yp;
+    u = occ | (occ >> 9) | (occ >> 18);
+    up = u >> 9;
+}
+
+// zero the 9-bit fields of `free` whose piece (one-hot field of c) is covered
+__device__ __forceinline__ uint32_t movable_fields(uint32_t covered_onehot, uint32_t free) {
+    uint32_t keep = ((covered_onehot & F0) ? 0u : F0) | ((covered_onehot & F1) ? 0u : F1) |
+                    ((covered_onehot & F2) ? 0u : F2);
+    return free & keep;
+}
+
+// 54-way legal-action mask of the player owning (x, y): Board.is_legal for a = 0..53
+// (board.py:82-115; gobblet.py:223-228).  bit a of (m1:m0), a = 9*(piece-1)+pos.
+__device__ __forceinline__ void legal_mask(uint32_t x, uint32_t y, uint32_t u, uint32_t up,
+                                           uint32_t &m0, uint32_t &m1) {
+    uint32_t free = ~u & B27;                    // field s: top piece absent or smaller than s
+    uint32_t mx = movable_fields(x & up, free);  // a covered piece may not move (board.py:101)
+    uint32_t my = movable_fields(y & up, free);
+    m0 = (mx & F0) | ((my & F0) << 9) | ((mx & F1) << 9) | ((my & F1) << 18);
+    m1 = ((my & F1) >> 14) | ((mx & F2) >> 14) | ((my & F2) >> 5);
+}
+
+// squares whose visible (top) piece belongs to the owner of (x, y): get_flatboard, board.py:159-177
+__device__ __forceinline__ uint32_t tops(uint32_t x, uint32_t y, uint32_t up) {
+    uint32_t v = (x | y) & ~up;
+    return (v | (v >> 9) | (v >> 18)) & 0x1FFu;
+}
+
+// Complete lines of both players at once.  Returns lm: bits 0..7 = lines of `to` complete, bits
+// 16..23 = lines of `tp`, bit i = line i in the reference's order (board.py:135-153):
+// (0,1,2) (3,4,5) (6,7,8) (0,3,6) (1,4,7) (2,5,8) (0,4,8) (2,4,6).
+__device__ __forceinline__ uint32_t line_bits(uint32_t to, uint32_t tp) {
+    uint32_t t = to | (tp << 16);
+    uint32_t t1 = t >> 1, t2 = t >> 2, t3 = t >> 3, t4 = t >> 4, t6 = t >> 6, t8 = t >> 8;
+    uint32_t a = t & t1 & t2 & 0x00490049u;  // bits 0,3,6 : lines 0,1,2
+    uint32_t b = t & t3 & t6 & 0x00070007u;  // bits 0,1,2 : lines 3,4,5
+    uint32_t d1 = t & t4 & t8 & 0x00010001u; // bit 0      : line 6
+    uint32_t d2 = t & t2 & t4 & 0x00040004u; // bit 2      : line 7
+    uint32_t ac = (a | (a >> 2) | (a >> 4)) & 0x00070007u;
+    return ac | (b << 3) | (d1 << 6) | (d2 << 5);
+}
+
+// check_for_winner (board.py:183-194): later lines overwrite earlier ones, so the winner is the
+// owner of the highest-index complete line.  A line cannot be complete for both players, hence the
+// two 8-bit line sets differ in their top bit and an unsigned compare decides.
+// Returns +1 (owner of `to`), -1 (owner of `tp`), 0; both = both players own a line (quirk Q1).
+__device__ __forceinline__ int winner_rel(uint32_t to, uint32_t tp, bool &both) {
+    uint32_t lm = line_bits(to, tp);
+    uint32_t lo = lm & 0xFFu, lp = lm >> 16;
+    both = lo && lp;
+    return (lo > lp) - (lp > lo);
+}
+
+// Board.play_turn for a LEGAL action of the mover (board.py:118-132) + bitmap update.
+__device__ __forceinline__ void apply_move(Env &e, uint32_t action) {
+    uint32_t k = (action * 57u) >> 9;   // piece-1 = action // 9   (board.py:67-68), exact for 0..53
+    uint32_t pos = action - 9u * k;     // action % 9              (board.py:63-64)
+    uint32_t f9 = 9u * (k >> 1);        // level offset            (board.py:71-79)
+    uint32_t field = 0x1FFu << f9, bit = 1u << (f9 + pos);
+    bool is_y = k & 1u;
+    uint32_t cur = is_y ? e.yo : e.xo;
+    uint32_t old = cur & field;         // previous location, if placed (board.py:128-130)
+    cur = (cur & ~field) | bit;
+    if (is_y) e.yo = cur; else e.xo = cur;
+    int b_old = 13 * (__ffs(old) - 1 - (int)f9) + (int)k;  // negative when the piece was in hand
+    uint32_t b_new = 13u * pos + k;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        e.s[j] = (e.s[j] & ~shl_clamp(1u, (uint32_t)b_old - 32u * j)) | shl_clamp(1u, b_new - 32u * j);
+}
+
+// hand the turn to the other player: swap the piece sets, swap the own/opponent halves of every
+// 13-bit square field, set plane 12 for player_2 (gobblet.py:182-185, :199-206, :246, :267)
+__device__ __forceinline__ void pass_turn(Env &e) {
+    uint32_t t;
+    t = e.xo; e.xo = e.xp; e.xp = t;
+    t = e.yo; e.yo = e.yp; e.yp = t;
+    e.agent ^= 1u;
+    const uint32_t a = e.agent ? 0xFFFFFFFFu : 0u;
+    const uint32_t s0 = e.s[0], s1 = e.s[1], s2 = e.s[2], s3 = e.s[3];
+    const uint32_t l0 = s0 << 6, l1 = __funnelshift_l(s0, s1, 6), l2 = __funnelshift_l(s1, s2, 6),
+                   l3 = __funnelshift_l(s2, s3, 6);
+    const uint32_t r0 = __funnelshift_r(s0, s1, 6), r1 = __funnelshift_r(s1, s2, 6),
+                   r2 = __funnelshift_r(s2, s3, 6), r3 = s3 >> 6;
+    e.s[0] = (l0 & OPP_0) | (r0 & OWN_0) | (a & P12_0);
+    e.s[1] = (l1 & OPP_1) | (r1 & OWN_1) | (a & P12_1);
+    e.s[2] = (l2 & OPP_2) | (r2 & OWN_2) | (a & P12_2);
+    e.s[3] = (l3 & OPP_3) | (r3 & OWN_3) | (a & P12_3);
+}
+
+// ---- one env.step (gobblet.py:231-273 + wrapper :110-117) -----------------------------------------
+struct StepResult {
+    int r1, r2;       // env.rewards[player_1], [player_2]
+    bool term, trunc; // flags of THIS step
+    bool acted;       // an action was consumed (false for dead envs / reset-only steps)
+};
+
+// (m0, m1) = legal mask of the mover BEFORE the move.  kFast drops the paths a random-legal rollout
+// with same-step auto-reset can never take (dead env, illegal action).
+template <bool kFast>
+__device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1, uint32_t action,
+                                               uint32_t flags, Stats &st) {
+    StepResult r = {0, 0, false, false, true};
+    const uint32_t autoreset = (flags >> 1) & 3u;
+    if (!kFast && e.done) {
+        r.acted = false;
+        if (autoreset == 2u) env_clear(e);          // next_step: this call only resets
+        else { r.term = true; r.trunc = e.trunc != 0; }
+        return r;
+    }
+    st.steps++;
+    const uint32_t mover = e.agent;
+    bool legal = true;
+    if (!kFast) {
+        uint32_t w = action < 32u ? m0 : m1;
+        legal = action < 54u && ((w >> (action & 31u)) & 1u);
+        if (!legal) {
+            st.illegal++;
+            if (!(flags & 1u)) {                    // TerminateIllegalWrapper, gobblet.py:114
+                if (mover == 0) r.r1 = -1; else r.r2 = -1;
+                r.term = r.trunc = true;
+                e.done = 1; e.trunc = 1;
+                st.episodes++; st.sumlen += e.plies; st.maxlen = max(st.maxlen, e.plies);
+                return r;
+            }
+        }
+    }
+    int w = 0; bool both = false;
+    if (legal) {
+        apply_move(e, action);
+        uint32_t u, up;
+        occupancy(e, u, up);
+        w = winner_rel(tops(e.xo, e.yo, up), tops(e.xp, e.yp, up), both);
+    }
+    pass_turn(e);
+    e.plies++;
+    if (w != 0) {                                   // gobblet.py:248-263
+        const uint32_t winner = w > 0 ? mover : mover ^ 1u;
+        r.r1 = winner == 0 ? 1 : -1;
+        r.r2 = -r.r1;
+        r.term = true;
+        e.done = 1;
+        st.episodes++; st.p1w += winner == 0; st.p2w += winner == 1;
+        st.sumlen += e.plies; st.both += both; st.maxlen = max(st.maxlen, e.plies);
+    }
+    return r;
+}
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al. 2011) -------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 draw_block(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t tag) {
+    return philox4x32_10(make_uint4((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)(step >> 2), tag),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint32_t pick_word(uint4 b, uint32_t i) {
+    return i == 0 ? b.x : i == 1 ? b.y : i == 2 ? b.z : b.w;
+}
+
+// index of the j-th (0-based) set bit of the 54-bit mask (m1:m0), j < popcount
+__device__ __forceinline__ uint32_t select_bit(uint32_t m0, uint32_t m1, uint32_t j) {
+    uint32_t c = __popc(m0);
+    bool hi = j >= c;
+    uint32_t w = hi ? m1 : m0, pos = hi ? 32u : 0u;
+    j -= hi ? c : 0u;
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) {
+        c = __popc(w & ((1u << sh) - 1u));
+        bool up = j >= c;
+        j -= up ? c : 0u;
+        w = up ? w >> sh : w;
+        pos += up ? sh : 0;
+    }
+    return pos;
+}
+
+// uniform legal action: j = floor(draw * count / 2^32)
+__device__ __forceinline__ uint32_t sample_action(uint32_t m0, uint32_t m1, uint32_t draw) {
+    uint32_t cnt = __popc(m0) + __popc(m1);
+    return cnt ? select_bit(m0, m1, __umulhi(draw, cnt)) : 0u;
+}
+
+// ---- emission: per-env bitmaps -> coalesced int8 tensors ---------------------------------------------
+// A warp owns 32 consecutive envs => 32*117 = 3744 contiguous observation bytes and 32*54 = 1728
+// contiguous mask bytes (both multiples of 16).  Each lane shifts its 117-bit / 54-bit bitmap to its
+// bit offset in the warp's packed stream, the boundary words are merged with one shuffle, the
+// stream is staged in shared memory (171 words), and every lane then turns 16 stream bits into 16
+// bytes (nibble * 0x00204081 & 0x01010101) and issues one fully coalesced 128-bit store.
+constexpr int OBS_WORDS = 117, MASK_WORDS = 54, STAGE_WORDS = 176;  // 171 used, padded to 16 B
+constexpr int OBS_VEC = 234, MASK_VEC = 108;                        // uint4 stores per warp
+
+struct LaneCfg {
+    uint32_t ofo, oso, mfo, mso;
+    bool on4, mn2;
+};
+
+__device__ __forceinline__ LaneCfg make_lane_cfg(uint32_t lane) {
+    LaneCfg c;
+    uint32_t o = 117u * lane, o2 = o + 117u, m = 54u * lane, m2 = m + 54u;
+    c.ofo = o >> 5; c.oso = o & 31u; c.on4 = ((o2 >> 5) - c.ofo) == 4u;
+    c.mfo = m >> 5; c.mso = m & 31u; c.mn2 = ((m2 >> 5) - c.mfo) == 2u;
+    return c;
+}
+
+__device__ __forceinline__ uint4 expand16(uint32_t h) {  // 16 bits -> 16 bytes of 0/1
+    const uint32_t M = 0x00204081u, K = 0x01010101u;
+    uint4 v;
+    v.x = ((h & 0xFu) * M) & K;
+    v.y = (((h >> 4) & 0xFu) * M) & K;
+    v.z = (((h >> 8) & 0xFu) * M) & K;
+    v.w = (((h >> 12) & 0xFu) * M) & K;
+    return v;
+}
+
+template <bool kStreaming>
+__device__ __forceinline__ void store16(int8_t *p, uint4 v) {
+    if (kStreaming) __stcs(reinterpret_cast<uint4 *>(p), v);
+    else *reinterpret_cast<uint4 *>(p) = v;
+}
+
+// stage: all 32 lanes of the warp must call (shuffle inside).  stage_buf = this warp's STAGE_WORDS.
+__device__ __forceinline__ void stage_bits(uint32_t *stage_buf, const LaneCfg &c, uint32_t lane,
+                                           const uint32_t (&s)[4], uint32_t m0, uint32_t m1) {
+    const uint32_t w0 = s[0] << c.oso, w1 = __funnelshift_l(s[0], s[1], c.oso),
+                   w2 = __funnelshift_l(s[1], s[2], c.oso), w3 = __funnelshift_l(s[2], s[3], c.oso),
+                   w4 = __funnelshift_l(s[3], 0u, c.oso);
+    uint32_t tail = c.on4 ? w4 : w3;            // partial word shared with the next lane
+    uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+    if (lane == 0) prev = 0;
+    stage_buf[c.ofo] = w0 | prev;
+    stage_buf[c.ofo + 1] = w1;
+    stage_buf[c.ofo + 2] = w2;
+    if (c.on4) stage_buf[c.ofo + 3] = w3;
+    const uint32_t v0 = m0 << c.mso, v1 = __funnelshift_l(m0, m1, c.mso), v2 = __funnelshift_l(m1, 0u, c.mso);
+    tail = c.mn2 ? v2 : v1;
+    prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+    if (lane == 0) prev = 0;
+    stage_buf[OBS_WORDS + c.mfo] = v0 | prev;
+    if (c.mn2) stage_buf[OBS_WORDS + c.mfo + 1] = v1;
+}
+
+// expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this warp
+// that exist (32 except in the last warp).
+template <bool kStreaming>
+__device__ __forceinline__ void emit_chunk(const uint32_t *stage_buf, uint32_t lane, int8_t *obs_chunk,
+                                           int8_t *mask_chunk, int nvalid) {
+    const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage_buf);
+    if (nvalid == 32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t q = lane + 32u * i;
+            if (i < 7 || q < OBS_VEC) store16<kStreaming>(obs_chunk + 16u * q, expand16(hb[q]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t q = lane + 32u * i;
+            if (i < 3 || q < MASK_VEC) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[2 * OBS_WORDS + q]));
+        }
+    } else {  // ragged last warp: vector stores while fully inside, bytes at the edge
+        const uint32_t ob = 117u * nvalid, mb = 54u * nvalid;
+        for (uint32_t q = lane; q < OBS_VEC; q += 32u) {
+            uint4 v = expand16(hb[q]);
+            if (16u * q + 16u <= ob) store16<kStreaming>(obs_chunk + 16u * q, v);
+            else {
+                const int8_t *b = reinterpret_cast<const int8_t *>(&v);
+                for (uint32_t j = 0; j < 16u && 16u * q + j < ob; ++j) obs_chunk[16u * q + j] = b[j];
+            }
+        }
+        for (uint32_t q = lane; q < MASK_VEC; q += 32u) {
+            uint4 v = expand16(hb[2 * OBS_WORDS + q]);
+            if (16u * q + 16u <= mb) store16<kStreaming>(mask_chunk + 16u * q, v);
+            else {
+                const int8_t *b = reinterpret_cast<const int8_t *>(&v);
+                for (uint32_t j = 0; j < 16u && 16u * q + j < mb; ++j) mask_chunk[16u * q + j] = b[j];
+            }
+        }
+    }
+}
+
+}  // namespace gbl

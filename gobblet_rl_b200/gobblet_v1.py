@@ -1,0 +1,161 @@
+"""`gobblet_v1` -- the reference's public module surface (gobblet_rl/gobblet_v1.py:1-3) on the GPU engine.
+
+    env(render_mode=None, args=None)       wrapper stack of gobblet.py:110-117 over raw_env
+    raw_env(render_mode=None, args=None)   PettingZoo AEC env (gobblet.py:123-290), a batch-of-1 view
+    GreedyGobbletPolicy(depth=2, seed=0)   greedy_policy.py:8-221
+    vec_env(num_envs, ...)                 NEW: vectorised entry point over torch CUDA tensors
+Rendering (pygame / text, gobblet.py:292-573) is out of scope; `render()` only warns, as the reference
+does for render_mode=None (gobblet.py:293-297).
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import _aec, _spaces
+from ._aec import AECEnv, agent_selector
+from .greedy_policy import GreedyGobbletPolicy, greedy_actions  # noqa: F401
+from .vec_env import HostVecEnv, VecEnv  # noqa: F401
+
+
+def vec_env(num_envs, device="cuda", seed=0, illegal_mode="terminate", autoreset="same_step", **kw):
+    return VecEnv(num_envs, device=device, seed=seed, illegal_mode=illegal_mode, autoreset=autoreset, **kw)
+
+
+def env(render_mode=None, args=None, device="cuda"):
+    e = raw_env(render_mode=render_mode, args=args, device=device)
+    e = _aec.TerminateIllegalWrapper(e, illegal_reward=-1)     # gobblet.py:114
+    e = _aec.AssertOutOfBoundsWrapper(e)                       # gobblet.py:115
+    e = _aec.OrderEnforcingWrapper(e)                          # gobblet.py:116
+    return e
+
+
+def parallel_env(**kwargs):
+    raise NotImplementedError("gobblet is turn based; the reference skips the parallel API too "
+                              "(tests/test_gobblet_env.py:37-42)")
+
+
+class _BoardView:
+    """`env.board` as callers of the reference read it: `.squares` float64[27] (board.py:33)."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    @property
+    def squares(self):
+        sq, _ = self._owner._vec.squares()
+        return sq[0].cpu().numpy().astype(np.float64)
+
+    def __str__(self):
+        return str(self.squares.reshape(3, 3, 3))
+
+
+class raw_env(AECEnv):
+    metadata = {
+        "render_modes": ["human", "rgb_array", "text", "text_full"],
+        "name": "gobblet_v1",
+        "is_parallelizable": True,
+        "render_fps": 60,
+        "has_manual_policy": True,
+    }
+
+    def __init__(self, render_mode=None, args=None, device="cuda"):
+        super().__init__()
+        # one env of the batched engine; illegal moves pass the turn like the reference's raw_env
+        self._vec = VecEnv(1, device=device, illegal_mode="pass", autoreset="off")
+        self.board = _BoardView(self)
+        self.board_size = 3
+        self.agents = ["player_1", "player_2"]
+        self.possible_agents = self.agents[:]
+        self.action_spaces = {i: _spaces.Discrete(54) for i in self.agents}
+        self.observation_spaces = {
+            i: _spaces.Dict({
+                "observation": _spaces.Box(low=0, high=1, shape=(3, 3, 13), dtype=np.int8),
+                "action_mask": _spaces.Box(low=0, high=1, shape=(54,), dtype=np.int8),
+            }) for i in self.agents
+        }
+        self.rewards = {i: 0 for i in self.agents}
+        self.terminations = {i: False for i in self.agents}
+        self.truncations = {i: False for i in self.agents}
+        self.infos = {i: {"legal_moves": list(range(0, 9))} for i in self.agents}
+        self._agent_selector = agent_selector(self.agents)
+        self.agent_selection = self._agent_selector.reset()
+        self.render_mode = render_mode
+        self.debug = args.debug if hasattr(args, "debug") else False
+        self.screen_width = args.screen_width if hasattr(args, "screen_width") else 640
+        self.screen_height = self.screen_width
+        self.screen = None
+        self._pull()
+
+    # one device->host read per step: obs(117) | mask(54) | rew(2) | terminated | agent_id
+    def _pull(self):
+        v = self._vec
+        packed = torch.cat([v.obs.reshape(-1).view(torch.uint8), v.mask.reshape(-1).view(torch.uint8),
+                            v.rew.reshape(-1).view(torch.uint8), v.terminated.view(torch.uint8),
+                            v.agent_id]).cpu().numpy()
+        self._obs = packed[:117].view(np.int8).reshape(3, 3, 13).copy()
+        self._mask = packed[117:171].view(np.int8).copy()
+        self._rew = packed[171:173].view(np.int8).astype(int)
+        self._term = bool(packed[173])
+        self._sel = int(packed[174])
+
+    def observe(self, agent):                                   # gobblet.py:179-215
+        selected = self.possible_agents[self._sel]
+        if agent == selected:
+            return {"observation": self._obs.copy(), "action_mask": self._mask.copy()}
+        # the other agent: planes from its own perspective (sign flip only, gobblet.py:182-185) and an
+        # all-zero mask (gobblet.py:209-213)
+        o = np.empty_like(self._obs)
+        o[..., 0:6], o[..., 6:12], o[..., 12] = self._obs[..., 6:12], self._obs[..., 0:6], 1 - self._obs[..., 12]
+        return {"observation": o, "action_mask": np.zeros(54, "int8")}
+
+    def observation_space(self, agent):
+        return self.observation_spaces[agent]
+
+    def action_space(self, agent):
+        return self.action_spaces[agent]
+
+    def _legal_moves(self):                                     # gobblet.py:223-228
+        return [int(a) for a in np.flatnonzero(self._mask)]
+
+    def step(self, action):                                     # gobblet.py:231-273
+        if self.terminations[self.agent_selection] or self.truncations[self.agent_selection]:
+            return self._was_dead_step(action)
+        self._vec.step(torch.tensor([int(action)], dtype=torch.int64, device=self._vec.device))
+        self._pull()
+        next_agent = self._agent_selector.next()
+        if self._term:
+            self.rewards[self.agents[0]] += int(self._rew[0])   # += / -=, zeroed only in reset (:255-260)
+            self.rewards[self.agents[1]] += int(self._rew[1])
+            self.terminations = {i: True for i in self.agents}
+        self._cumulative_rewards[self.agent_selection] = 0
+        self.agent_selection = next_agent
+        self._accumulate_rewards()
+        self.turn += 1
+        self.action = action
+        if self.render_mode in ["human", "text", "text_full", "rgb_array"]:
+            self.render()
+
+    def reset(self, seed=None, return_info=False, options=None):   # gobblet.py:275-290
+        self._vec.reset()
+        self._pull()
+        self.agents = self.possible_agents[:]
+        self.rewards = {i: 0 for i in self.agents}
+        self._cumulative_rewards = {i: 0 for i in self.agents}
+        self.terminations = {i: False for i in self.agents}
+        self.truncations = {i: False for i in self.agents}
+        self.infos = {i: {} for i in self.agents}
+        self._agent_selector.reinit(self.agents)
+        self._agent_selector.reset()
+        self.agent_selection = self._agent_selector.reset()
+        self.turn = 0
+        self.action = -1
+
+    def render(self):
+        if self.render_mode is None:
+            warnings.warn("You are calling render method without specifying any render mode.")
+            return
+        raise NotImplementedError("pygame / text rendering is out of scope of the B200 engine (SURVEY.md section 2 #3)")
+
+    def close(self):
+        self.screen = None

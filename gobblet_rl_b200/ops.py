@@ -1,0 +1,188 @@
+"""ctypes binding of libgobblet_b200.so (C ABI: include/gobblet_b200.h) + torch custom ops.
+
+PyTorch is plumbing here: it owns device memory and streams; every computation happens in the
+sm_100a kernels behind the C ABI.  There is NO fallback: if the library cannot be loaded (or built
+with nvcc) importing this module raises.
+"""
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from .csrc import build as _build
+
+OBS_BYTES, MASK_BYTES, STATE_BYTES, NUM_ACTIONS = 117, 54, 16, 54
+ILLEGAL_TERMINATE, ILLEGAL_PASS = 0x0, 0x1
+AUTORESET_OFF, AUTORESET_SAME_STEP, AUTORESET_NEXT_STEP = 0 << 1, 1 << 1, 2 << 1
+STORE_DEFAULT_POLICY = 0x8
+ABI_VERSION = 1
+
+_ILLEGAL = {"terminate": ILLEGAL_TERMINATE, "pass": ILLEGAL_PASS}
+_AUTORESET = {"off": AUTORESET_OFF, "same_step": AUTORESET_SAME_STEP, "next_step": AUTORESET_NEXT_STEP}
+
+
+def make_flags(illegal_mode="terminate", autoreset="same_step", streaming_stores=True):
+    return _ILLEGAL[illegal_mode] | _AUTORESET[autoreset] | (0 if streaming_stores else STORE_DEFAULT_POLICY)
+
+
+def _load():
+    try:
+        path = _build.build()
+    except Exception as exc:  # no nvcc and no prebuilt library: fail loudly, never fall back
+        raise RuntimeError(
+            "gobblet_rl_b200: libgobblet_b200.so is missing and could not be built with nvcc "
+            f"({exc}). The engine has no CPU fallback.") from exc
+    lib = C.CDLL(path)
+    vp, i64, i32, u64, u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32
+    sigs = {
+        "gbl_abi_version": (C.c_int, []),
+        "gbl_last_error": (C.c_char_p, []),
+        "gbl_reset": (C.c_int, [vp, i64, vp]),
+        "gbl_reset_masked": (C.c_int, [vp, vp, i64, vp]),
+        "gbl_observe": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+        "gbl_step": (C.c_int, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, u32, vp]),
+        "gbl_rollout_random": (C.c_int, [vp, i64, i32, u64, u64, u64, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, u32, vp]),
+        "gbl_sample_legal": (C.c_int, [vp, u64, u64, u64, vp, i64, vp]),
+        "gbl_greedy": (C.c_int, [vp, vp, vp, i32, u64, u64, vp, vp, vp, vp, i64, vp]),
+        "gbl_export_squares": (C.c_int, [vp, vp, vp, i64, vp]),
+        "gbl_import_squares": (C.c_int, [vp, vp, vp, i64, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.gbl_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libgobblet_b200.so ABI {lib.gbl_abi_version()} != expected {ABI_VERSION}")
+    return lib, path
+
+
+LIB, LIB_PATH = _load()
+EXPORTED_SYMBOLS = ("gbl_abi_version", "gbl_last_error", "gbl_reset", "gbl_reset_masked", "gbl_observe",
+                    "gbl_step", "gbl_rollout_random", "gbl_sample_legal", "gbl_greedy", "gbl_export_squares",
+                    "gbl_import_squares")
+
+
+class GobbletError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise GobbletError(f"libgobblet_b200 error {rc}: {LIB.gbl_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise GobbletError("gobblet_rl_b200 ops need CUDA tensors (there is no CPU path)")
+        if not t.is_contiguous():
+            raise GobbletError("gobblet_rl_b200 ops need contiguous tensors")
+        if dev is not None and t.device != dev:
+            raise GobbletError("all tensors of one call must live on the same device")
+        dev = t.device
+    return dev
+
+
+# ---- torch custom ops (schema + fake impls so the engine composes with torch.compile / graphs) ------
+@torch.library.custom_op("gobblet_b200::reset", mutates_args=("state",))
+def reset(state: torch.Tensor, which: Optional[torch.Tensor] = None) -> None:
+    dev = _need_cuda(state, which)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_reset_masked(_ptr(state), _ptr(which), state.shape[0], _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::observe", mutates_args=("obs", "mask", "agent_id"))
+def observe(state: torch.Tensor, obs: torch.Tensor, mask: torch.Tensor, agent_id: Optional[torch.Tensor]) -> None:
+    dev = _need_cuda(state, obs, mask, agent_id)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_observe(_ptr(state), _ptr(obs), _ptr(mask), _ptr(agent_id), state.shape[0], _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::step", mutates_args=("state", "obs", "mask", "rew", "terminated", "truncated",
+                                                             "agent_id", "final_obs", "final_mask", "stats"))
+def step(state: torch.Tensor, actions: torch.Tensor, obs: torch.Tensor, mask: torch.Tensor,
+         rew: Optional[torch.Tensor], terminated: Optional[torch.Tensor], truncated: Optional[torch.Tensor],
+         agent_id: Optional[torch.Tensor], final_obs: Optional[torch.Tensor], final_mask: Optional[torch.Tensor],
+         stats: Optional[torch.Tensor], flags: int) -> None:
+    dev = _need_cuda(state, actions, obs, mask, rew, terminated, truncated, agent_id, final_obs, final_mask, stats)
+    if actions.dtype not in (torch.uint8, torch.int32, torch.int64) or actions.numel() != state.shape[0]:
+        raise GobbletError("actions must be uint8 / int32 / int64 with one entry per env")
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_step(_ptr(state), _ptr(actions), actions.element_size(), _ptr(obs), _ptr(mask), _ptr(rew),
+                            _ptr(terminated), _ptr(truncated), _ptr(agent_id), _ptr(final_obs), _ptr(final_mask),
+                            _ptr(stats), state.shape[0], flags, _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::rollout_random",
+                         mutates_args=("state", "obs_out", "mask_out", "rew_out", "term_out", "agent_out",
+                                       "action_log", "stats"))
+def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, step_base: int,
+                   obs_out: Optional[torch.Tensor], mask_out: Optional[torch.Tensor],
+                   rew_out: Optional[torch.Tensor], term_out: Optional[torch.Tensor],
+                   agent_out: Optional[torch.Tensor], action_log: Optional[torch.Tensor],
+                   stats: Optional[torch.Tensor], flags: int) -> None:
+    """obs_out [ring, n, 3, 3, 13] / mask_out [ring, n, 54] (possibly views of padded slots)."""
+    dev = _need_cuda(state, rew_out, term_out, agent_out, action_log, stats)
+    n = state.shape[0]
+    ring, so, sm = 1, 0, 0
+    if obs_out is not None:
+        if not (obs_out.is_cuda and mask_out is not None and mask_out.is_cuda):
+            raise GobbletError("obs_out / mask_out must both be CUDA tensors")
+        ring = obs_out.shape[0]
+        so, sm = obs_out.stride(0), mask_out.stride(0)          # int8 => element stride == bytes
+        if obs_out[0].numel() != n * OBS_BYTES or not obs_out[0].is_contiguous() or not mask_out[0].is_contiguous():
+            raise GobbletError("each ring slot must be a contiguous [n,3,3,13] / [n,54] int8 block")
+    for t in (rew_out, term_out, agent_out):
+        if t is not None and t.shape[0] != ring:
+            raise GobbletError("per-step outputs must share the ring length of obs_out")
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(obs_out),
+                                      _ptr(mask_out), so, sm, ring, _ptr(rew_out), _ptr(term_out), _ptr(agent_out),
+                                      _ptr(action_log), _ptr(stats), flags, _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::sample_legal", mutates_args=("act",))
+def sample_legal(mask: torch.Tensor, seed: int, env_id_base: int, step: int, act: torch.Tensor) -> None:
+    dev = _need_cuda(mask, act)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_sample_legal(_ptr(mask), seed & (2**64 - 1), env_id_base, step, _ptr(act), act.numel(),
+                                    _stream(mask)))
+
+
+@torch.library.custom_op("gobblet_b200::greedy", mutates_args=("act", "chosen", "cand", "used_fallback"))
+def greedy(obs: torch.Tensor, mask: torch.Tensor, prev3: Optional[torch.Tensor], depth: int, seed: int,
+           ctr_base: int, act: torch.Tensor, chosen: Optional[torch.Tensor], cand: Optional[torch.Tensor],
+           used_fallback: Optional[torch.Tensor]) -> None:
+    dev = _need_cuda(obs, mask, prev3, act, chosen, cand, used_fallback)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_greedy(_ptr(obs), _ptr(mask), _ptr(prev3), depth, seed & (2**64 - 1), ctr_base, _ptr(act),
+                              _ptr(chosen), _ptr(cand), _ptr(used_fallback), act.numel(), _stream(obs)))
+
+
+@torch.library.custom_op("gobblet_b200::export_squares", mutates_args=("squares", "agent"))
+def export_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor]) -> None:
+    dev = _need_cuda(state, squares, agent)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_export_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::import_squares", mutates_args=("state",))
+def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor]) -> None:
+    dev = _need_cuda(state, squares, agent)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_import_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
+
+
+for _op in (reset, observe, step, rollout_random, sample_legal, greedy, export_squares, import_squares):
+    _op.register_fake(lambda *a, **k: None)

@@ -1,0 +1,47 @@
+"""Multi-GPU sharding: environments are independent, so ranks own contiguous blocks of global env ids
+and exchange NOTHING per step.  The only collective is one end-of-run all-reduce of the int64[8]
+episode statistics (slots 0-6 summed, slot 7 = max episode length maxed) over NCCL (gloo in CPU tests).
+Because the Philox counters are keyed by GLOBAL env id, any world size plays the same games."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total_envs: int, rank: int, world_size: int):
+    """Contiguous block [lo, hi) of global env ids owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(int(total_envs), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def init_from_env(backend=None):
+    """One process per GPU, launched by torchrun: reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Whole-job statistics from per-rank int64[8] vectors (the run's single collective)."""
+    out = stats.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        sums, mx = out[:7].clone(), out[7:].clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        out[:7], out[7:] = sums, mx
+    return out
+
+
+def sharded_vec_env(total_envs: int, rank: int, world_size: int, device=None, **kw):
+    from .vec_env import VecEnv
+
+    lo, hi = shard_range(total_envs, rank, world_size)
+    return VecEnv(hi - lo, device=device if device is not None else "cuda", env_id_base=kw.pop("env_id_base", 0) + lo, **kw)

@@ -1,0 +1,127 @@
+/*
+ * gobblet_b200.h -- C ABI of libgobblet_b200.so (sm_100a).
+ *
+ * The reference (elliottower/gobblet-rl) is pure Python and has no FFI; the boundary below is the
+ * set of entry points a binding for its per-step hot path would need.  Each entry cites the
+ * reference interface it replaces (paths under the reference repo).  Plain pointers and sizes only:
+ * no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the caller's current CUDA device unless it says "host";
+ *   - the caller owns all buffers; the library allocates nothing;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL =
+ *     legacy default stream); functions are re-entrant and keep no global mutable state;
+ *   - return value 0 = success, negative = error (GBL_E_*), message via gbl_last_error()
+ *     (thread-local); no C++ exception crosses the ABI;
+ *   - actions outside [0,54) are treated as illegal moves, never as undefined behaviour.
+ *
+ * Layouts
+ *   state  : n * 16 bytes, 16-byte aligned.  Two little-endian u64 per env:
+ *              w0 = X1 | Y1<<27 | meta_lo<<54      w1 = X2 | Y2<<27 | meta_hi<<54
+ *            Xp/Yp = 27-bit boards of player p's odd/even pieces (pieces 1,3,5 / 2,4,6 of
+ *            board.py:33), bit 9*(size-1)+pos -- the reference's own `squares` index.
+ *            meta (20 bits) = agent_selection | done<<1 | truncated<<2 | plies<<3 (saturating).
+ *   obs    : int8 [n][3][3][13], byte pos*13+c   (gobblet.py:188-208), 16-byte aligned base
+ *   mask   : int8 [n][54]                        (gobblet.py:209-213, :223-228), 16-byte aligned base
+ *   rew2   : int8 [n][2] = env.rewards[player_1], env.rewards[player_2]   (gobblet.py:255-260)
+ *   stats  : int64[8] accumulated with atomics: episodes, player_1 wins, player_2 wins, live steps,
+ *            sum of episode lengths, illegal moves, both-line endings, max episode
+ *            length (slot 7 is a max, not a sum).
+ */
+#ifndef GOBBLET_B200_H
+#define GOBBLET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GBL_API __attribute__((visibility("default")))
+#else
+#define GBL_API
+#endif
+
+#define GBL_ABI_VERSION 1
+#define GBL_OBS_BYTES 117
+#define GBL_MASK_BYTES 54
+#define GBL_STATE_BYTES 16
+#define GBL_NUM_ACTIONS 54
+
+/* flags */
+#define GBL_ILLEGAL_TERMINATE 0x0u /* env(): TerminateIllegalWrapper(illegal_reward=-1), gobblet.py:114 */
+#define GBL_ILLEGAL_PASS 0x1u      /* raw_env: board untouched, turn passes, board.py:125-126 + gobblet.py:244-270 */
+#define GBL_AUTORESET_OFF (0u << 1)
+#define GBL_AUTORESET_SAME_STEP (1u << 1)
+#define GBL_AUTORESET_NEXT_STEP (2u << 1)
+#define GBL_AUTORESET_MASK (3u << 1)
+#define GBL_STORE_DEFAULT_POLICY 0x8u /* use plain st.global instead of streaming (evict-first) stores */
+
+/* errors */
+#define GBL_E_INVALID (-1) /* bad argument (null pointer, misalignment, n < 0 ...) */
+#define GBL_E_CUDA (-2)    /* CUDA runtime error; text in gbl_last_error() */
+
+GBL_API int gbl_abi_version(void);
+GBL_API const char *gbl_last_error(void);
+
+/* raw_env.reset(): fresh Board, player_1 to move, turn 0  (gobblet.py:275-290, board.py:33) */
+GBL_API int gbl_reset(void *state, int64_t n, void *stream);
+/* reset the envs with which[i] != 0 (Tianshou venv.reset(ids), collector_manual_policy.py:132-145) */
+GBL_API int gbl_reset_masked(void *state, const uint8_t *which, int64_t n, void *stream);
+
+/* raw_env.observe(agent_selection) for every env: planes + live 54-way mask
+ * (gobblet.py:179-215, :223-228 -> 54 x Board.is_legal, board.py:82-115). agent_id nullable. */
+GBL_API int gbl_observe(const void *state, int8_t *obs, int8_t *mask, uint8_t *agent_id, int64_t n,
+                void *stream);
+
+/* env.step(action); env.last() for every env (gobblet.py:231-273; Board.play_turn board.py:118-132;
+ * check_for_winner board.py:183-194; wrapper gobblet.py:110-117), then observe the new
+ * agent_selection.  actions: n integers of action_bytes (1 = uint8, 4 = int32, 8 = int64) each.
+ * Nullable: rew2, terminated, truncated, agent_id, final_obs/final_mask (terminal observation that
+ * same-step auto-reset would otherwise replace), stats. */
+GBL_API int gbl_step(void *state, const void *actions, int32_t action_bytes, int8_t *obs, int8_t *mask,
+             int8_t *rew2, uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id,
+             int8_t *final_obs, int8_t *final_mask, int64_t *stats, int64_t n, uint32_t flags,
+             void *stream);
+
+/* Fused random-legal-action rollout: the example_basic.py:50-67 / main_random.py:23-37 loop for n
+ * lockstep envs and T steps in ONE launch, state register-resident.  Action of env i at absolute
+ * step s = step_base + t: j = mulhi(Philox4x32-10(key = seed, ctr = (env_id_base+i, s>>2, 0))[s&3],
+ * popcount(mask)), the j-th legal action in ascending order (uniform over the mask, as
+ * example_basic.py:58-61).  Per step the next observation and mask are written to ring slot
+ * (step_base+t) % ring of obs_out / mask_out (slot strides in bytes, multiples of 16).
+ * Nullable: obs_out+mask_out (simulate only), rew_out [ring][n][2], term_out [ring][n],
+ * agent_out [ring][n], action_log [T][n] (255 = no action), stats. */
+GBL_API int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_t env_id_base,
+                       uint64_t step_base, int8_t *obs_out, int8_t *mask_out,
+                       int64_t obs_slot_stride, int64_t mask_slot_stride, int32_t ring,
+                       int8_t *rew_out, uint8_t *term_out, uint8_t *agent_out, uint8_t *action_log,
+                       int64_t *stats, uint32_t flags, void *stream);
+
+/* Uniform sample over each mask row with the same Philox stream as the rollout
+ * (random_admissible_policy_rllib.py:23-30, example_basic.py:58-61).  act[i] = -1 for an empty row. */
+GBL_API int gbl_sample_legal(const int8_t *mask, uint64_t seed, uint64_t env_id_base, uint64_t step,
+                     int32_t *act, int64_t n, void *stream);
+
+/* GreedyGobbletPolicy(depth).compute_action for n boards, one warp per board
+ * (greedy_policy.py:38-221; depth 1 or 2).  prev3 (nullable): int16 [n][3], the agent's last three
+ * actions, -1 = none (greedy_policy.py:211-214).  Outputs (all nullable except act):
+ *   act[i]     final action (Philox pick among the candidates when the fallback fires; -1 if the mask is empty)
+ *   chosen[i]  choice before the random fallback, -1 = None
+ *   cand[i]    bit a set <=> a in actions_depth1 (what np.random.choice draws from, :217)
+ *   used_fallback[i] */
+GBL_API int gbl_greedy(const int8_t *obs, const int8_t *mask, const int16_t *prev3, int32_t depth,
+               uint64_t seed, uint64_t ctr_base, int32_t *act, int32_t *chosen, uint64_t *cand,
+               uint8_t *used_fallback, int64_t n, void *stream);
+
+/* Debug / interchange views of the reference's own state array (board.py:33):
+ * squares int8 [n][27] signed piece numbers, agent uint8 [n] (0 = player_1 to move). */
+GBL_API int gbl_export_squares(const void *state, int8_t *squares, uint8_t *agent, int64_t n, void *stream);
+GBL_API int gbl_import_squares(void *state, const int8_t *squares, const uint8_t *agent, int64_t n,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOBBLET_B200_H */

@@ -1,0 +1,163 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gobblet_b200.h declares,
+the product never touches oracle/, the AEC plumbing behaves, and the N>1 path (sharding + the single
+statistics all-reduce) works over gloo with world_size 2.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gobblet_rl_b200 import ops
+    header = open(os.path.join(REPO, "include", "gobblet_b200.h")).read()
+    declared = sorted(set(re.findall(r"GBL_API\s+(?:const\s+)?\w+\s*\*?\s*(gbl_\w+)\s*\(", header)))
+    assert len(declared) == 11 and set(declared) == set(ops.EXPORTED_SYMBOLS)
+    lib = C.CDLL(ops.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gbl_abi_version() == 1
+    # the shipped SASS is sm_100a only, built from hand-written kernels (no PTX JIT, no other arch)
+    out = subprocess.run(["cuobjdump", "-lelf", ops.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_argument_validation_needs_no_gpu():
+    from gobblet_rl_b200 import ops
+    lib = ops.LIB
+    assert lib.gbl_reset(None, 5, None) == -1 and b"gbl_reset" in lib.gbl_last_error()
+    assert lib.gbl_reset(None, 0, None) == 0                                   # empty batch is a no-op
+    assert lib.gbl_observe(None, None, None, None, -1, None) == -1
+    assert lib.gbl_greedy(None, None, None, 3, 0, 0, None, None, None, None, 1, None) == -1
+    with pytest.raises(ops.GobbletError):
+        ops.observe(torch.zeros((4, 2), dtype=torch.int64), torch.zeros((4, 3, 3, 13), dtype=torch.int8),
+                    torch.zeros((4, 54), dtype=torch.int8), None)              # CPU tensors: no fallback
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for root, _, files in os.walk(os.path.join(REPO, "gobblet_rl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/|gobblet_oracle|reference_loader", text, re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_aec_plumbing_with_a_scripted_env():
+    """_aec (used when PettingZoo is absent): last(), reward accumulation, dead steps, the three wrappers."""
+    from gobblet_rl_b200 import _aec, _spaces
+
+    class Scripted(_aec.AECEnv):
+        metadata = {"name": "scripted"}
+
+        def __init__(self):
+            super().__init__()
+            self.possible_agents = ["a", "b"]
+            self.action_spaces = {x: _spaces.Discrete(3) for x in self.possible_agents}
+            self.observation_spaces = {x: _spaces.Dict({"action_mask": _spaces.Box(0, 1, (3,), np.int8)})
+                                       for x in self.possible_agents}
+            self._sel = _aec.agent_selector(self.possible_agents)
+
+        def reset(self, seed=None, return_info=False, options=None):
+            self.agents = self.possible_agents[:]
+            self.rewards = {x: 0 for x in self.agents}
+            self._cumulative_rewards = {x: 0 for x in self.agents}
+            self.terminations = {x: False for x in self.agents}
+            self.truncations = {x: False for x in self.agents}
+            self.infos = {x: {} for x in self.agents}
+            self._sel.reinit(self.agents)
+            self.agent_selection = self._sel.reset()
+            self.count = 0
+
+        def observe(self, agent):
+            return {"action_mask": np.array([1, 1, 0], np.int8)}
+
+        def step(self, action):
+            if self.terminations[self.agent_selection]:
+                return self._was_dead_step(action)
+            self.count += 1
+            nxt = self._sel.next()
+            if action == 1:
+                self.rewards = {"a": 1, "b": -1}
+                self.terminations = {x: True for x in self.agents}
+            self._cumulative_rewards[self.agent_selection] = 0
+            self.agent_selection = nxt
+            self._accumulate_rewards()
+
+    env = _aec.OrderEnforcingWrapper(_aec.AssertOutOfBoundsWrapper(_aec.TerminateIllegalWrapper(Scripted(), -1)))
+    with pytest.raises(AssertionError):
+        env.step(0)
+    env.reset()
+    assert env.agent_selection == "a" and env.last()[1:4] == (0, False, False)
+    env.step(0)
+    assert env.agent_selection == "b"
+    env.step(1)                                            # b ends the game: a +1, b -1
+    assert [env.last()[1]] == [1] and env.agent_selection == "a" and all(env.terminations.values())
+    env.step(None)
+    assert env.agents == ["b"] and env.last()[1] == -1
+    env.step(None)
+    assert env.agents == [] and list(env.agent_iter()) == []
+    env.reset()
+    env.step(2)                                            # masked out -> illegal-move termination
+    assert env.rewards == {"a": -1.0, "b": 0} and all(env.truncations.values()) and env.agent_selection == "a"
+    with pytest.raises(ValueError):
+        env.step(0)
+    env.reset()
+    with pytest.raises(AssertionError):
+        env.step(7)                                        # out of bounds
+    s = _spaces.Discrete(54)
+    assert s.contains(np.int64(5)) and s.contains(np.array(53)) and not s.contains(54) and not s.contains(1.0)
+
+
+def test_shard_ranges_cover_all_envs():
+    from gobblet_rl_b200.sharding import shard_range
+    for total in (0, 1, 7, 1 << 20, (1 << 20) + 5):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {repo!r})
+import numpy as np, torch, torch.distributed as dist
+from gobblet_rl_b200.sharding import init_from_env, shard_range, all_reduce_stats
+from oracle import oracle as O            # the CPU stand-in for the per-rank engine in this host-logic test
+rank, local, world = init_from_env(backend="gloo")
+total, T, seed = 300, 40, 17
+lo, hi = shard_range(total, rank, world)
+v = O.VecOracle(hi - lo)
+out = v.rollout_random(T, seed=seed, env_id_base=lo, per_step=False)
+merged = all_reduce_stats(torch.from_numpy(v.stats.copy()))
+if rank == 0:
+    whole = O.VecOracle(total)
+    w = whole.rollout_random(T, seed=seed, per_step=False)
+    assert merged.tolist() == whole.stats.tolist(), (merged.tolist(), whole.stats.tolist())
+    assert np.array_equal(out["actions"], w["actions"][:, lo:hi])
+    print("OK", merged.tolist())
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_statistics_all_reduce(tmp_path):
+    """world_size 2 over gloo: shards keyed by GLOBAL env id replay the same games as one rank, and the
+    single SUM/MAX all-reduce reproduces the whole-job statistics."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(repo=REPO))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "OK" in res.stdout

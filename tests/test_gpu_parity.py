@@ -1,0 +1,227 @@
+"""Parity of the CUDA engine (through the C ABI / torch custom ops) with the CPU oracle. Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gv1():
+    from gobblet_rl_b200 import gobblet_v1
+    assert torch.cuda.is_available()
+    return gobblet_v1
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("autoreset", ["same_step", "off", "next_step"])
+@pytest.mark.parametrize("n,T", [(1000, 64), (32, 20), (1, 40), (4097, 12)])
+def test_fused_rollout_bit_exact(gv1, autoreset, n, T):
+    """obs, masks, rewards, terminations, agent ids, sampled actions and statistics of the fused
+    rollout kernel == oracle replay (same seed, same global env ids)."""
+    v = gv1.vec_env(n, seed=11, autoreset=autoreset, env_id_base=12345)
+    v.step_count = 6
+    got = v.rollout_random(T, ring=T, per_step=True, log_actions=True)
+    o = O.VecOracle(n, "terminate", autoreset)
+    want = o.rollout_random(T, seed=11, env_id_base=12345, step_base=6)
+    # ring slot of absolute step s is s % ring
+    order = [(6 + t) % T for t in range(T)]
+    assert np.array_equal(_np(got["actions"]), want["actions"])
+    assert np.array_equal(_np(got["obs"])[order], want["obs"])
+    assert np.array_equal(_np(got["mask"])[order], want["mask"])
+    assert np.array_equal(_np(got["rew"])[order], want["rew"])
+    assert np.array_equal(_np(got["terminated"])[order], want["terminated"])
+    assert np.array_equal(_np(got["agent_id"])[order], want["agent_id"])
+    assert v.stats.tolist() == o.stats.tolist()
+    sq, agent = v.squares()
+    assert np.array_equal(_np(sq), o.squares())
+
+
+def test_rollout_split_equals_whole(gv1):
+    """State round-trips through HBM: 3 launches of 7+1+25 steps == one launch of 33."""
+    a = gv1.vec_env(777, seed=3)
+    b = gv1.vec_env(777, seed=3)
+    whole = a.rollout_random(33, ring=33, log_actions=True)
+    parts = [b.rollout_random(t, ring=1, log_actions=True)["actions"] for t in (7, 1, 25)]
+    assert torch.equal(whole["actions"], torch.cat(parts))
+    assert torch.equal(a.state, b.state) and torch.equal(a.stats, b.stats)
+
+
+@pytest.mark.parametrize("illegal_mode", ["terminate", "pass"])
+@pytest.mark.parametrize("autoreset", ["same_step", "off", "next_step"])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.uint8])
+def test_step_arbitrary_actions_bit_exact(gv1, illegal_mode, autoreset, dtype):
+    n, T = 333, 50
+    rng = np.random.default_rng(7)
+    v = gv1.vec_env(n, illegal_mode=illegal_mode, autoreset=autoreset)
+    o = O.VecOracle(n, illegal_mode, autoreset)
+    _, mask, _ = o.reset()
+    fobs = torch.zeros((n, 3, 3, 13), dtype=torch.int8, device="cuda")
+    fmask = torch.zeros((n, 54), dtype=torch.int8, device="cuda")
+    for t in range(T):
+        acts = np.array([rng.choice(np.flatnonzero(m)) for m in mask], np.int64)
+        bad = rng.random(n) < 0.1
+        lo = -3 if dtype == torch.int64 else 0
+        acts[bad] = rng.integers(lo, 60, bad.sum())
+        g = v.step(torch.as_tensor(acts).to(dtype).cuda(), final=(fobs, fmask))
+        w = o.step(acts, want_final=True)
+        for i, name in enumerate(("obs", "mask", "rew", "terminated", "truncated", "agent_id")):
+            assert np.array_equal(_np(g[i]), w[i]), (t, name)
+        if autoreset == "same_step":
+            assert np.array_equal(_np(fobs), w[6]) and np.array_equal(_np(fmask), w[7])
+        mask = w[1]
+    assert v.stats.tolist() == o.stats.tolist() and v.stats[5] > 0
+
+
+def test_int32_actions_and_reset_ids(gv1):
+    v = gv1.vec_env(64, autoreset="off")
+    o = O.VecOracle(64, "terminate", "off")
+    rng = np.random.default_rng(1)
+    _, mask, _ = o.reset()
+    for t in range(30):
+        acts = np.array([rng.choice(np.flatnonzero(m)) for m in mask], np.int64)
+        g = v.step(torch.as_tensor(acts, dtype=torch.int32).cuda())
+        w = o.step(acts)
+        assert np.array_equal(_np(g[0]), w[0]) and np.array_equal(_np(g[3]), w[3])
+        mask = w[1]
+    done = g[3].clone()
+    assert done.any() and not done.all()
+    obs, mask_t, agent = v.reset(done)                      # Tianshou order: reset finished envs only
+    assert (obs[done] == 0).all() and (mask_t[done] == 1).all() and (agent[done] == 0).all()
+    assert np.array_equal(_np(obs[~done]), w[0][~_np(done)])
+    idx = torch.nonzero(~done).flatten()[:3]
+    v.reset(idx)
+    assert (v.obs[idx] == 0).all()
+
+
+def test_reference_known_answers_and_golden_traces(gv1, golden):
+    k = golden("reference_kat")
+    v = gv1.vec_env(1, illegal_mode="pass", autoreset="off")
+    _, mask, _ = v.reset()
+    assert np.array_equal(_np(mask).astype(bool), k["output0"].astype(bool))
+    for i, a in enumerate(k["actions"]):
+        _, mask, *_ = v.step(torch.tensor([a]))
+        assert np.array_equal(_np(mask).astype(bool), k[f"output{i + 1}"].astype(bool))
+    assert np.flatnonzero(_np(mask)[0]).tolist() == k["output6"].tolist()
+    v.step(torch.tensor([int(k["illegal_action"])]))
+    assert np.array_equal(_np(v.squares()[0])[0].reshape(3, 3, 3), k["output8"].astype(np.int8))
+    for name in ("env_traces", "env_traces_illegal"):
+        g = golden(name)
+        starts = g["game_start"]
+        for gi in range(len(starts) - 1):
+            v.reset()
+            for i in range(starts[gi], starts[gi + 1]):
+                obs, mask, rew, term, trunc, agent = v.step(torch.tensor([g["actions"][i]]))
+                assert np.array_equal(_np(obs)[0], g["obs"][i]) and np.array_equal(_np(mask)[0], g["mask"][i])
+                assert _np(rew)[0].tolist() == g["rew"][i].tolist() and bool(term[0]) == bool(g["term"][i])
+                assert int(agent[0]) == int(g["agent_id"][i])
+                assert np.array_equal(_np(v.squares()[0])[0], g["squares"][i])
+
+
+def test_import_export_and_observe_random_positions(gv1):
+    """Arbitrary reachable positions (incl. finished games) loaded through import_squares."""
+    o = O.VecOracle(3000, "terminate", "off")
+    o.rollout_random(14, seed=2, per_step=False)
+    sq = o.squares()
+    _, _, agent = o.observe()
+    v = gv1.vec_env(3000, autoreset="off")
+    obs, mask, ag = v.set_squares(sq, agent)
+    wobs, wmask, wagent = o.observe()
+    assert np.array_equal(_np(obs), wobs) and np.array_equal(_np(mask), wmask) and np.array_equal(_np(ag), wagent)
+    back, ag2 = v.squares()
+    assert np.array_equal(_np(back), sq) and np.array_equal(_np(ag2), agent)
+
+
+def test_sample_legal_matches_oracle(gv1):
+    from gobblet_rl_b200 import ops
+    rng = np.random.default_rng(0)
+    mask = (rng.random((500, 54)) < 0.4).astype(np.int8)
+    mask[0] = 0
+    mask[1] = 1
+    act = torch.zeros(500, dtype=torch.int32, device="cuda")
+    ops.sample_legal(torch.as_tensor(mask).cuda(), 99, 1 << 33, 6, act)
+    want = [O.pick(m, O.draw(99, (1 << 33) + i, 6)) if m.any() else -1 for i, m in enumerate(mask)]
+    assert _np(act).tolist() == want
+
+
+@pytest.mark.parametrize("depth", [1, 2])
+def test_greedy_matches_oracle_on_rollout_positions(gv1, depth):
+    """Warp-per-board search == literal restatement of greedy_policy.py on 4000 positions,
+    including positions of finished games and histories that trip the repetition rule."""
+    n = 4000
+    o = O.VecOracle(n, "terminate", "off")
+    o.rollout_random(9, seed=4, per_step=False)
+    obs, mask, _ = o.observe()
+    rng = np.random.default_rng(5)
+    prev3 = rng.integers(-1, 54, (n, 3)).astype(np.int16)
+    act, chosen, cand, fb = gv1.greedy_actions(torch.as_tensor(obs).cuda(), torch.as_tensor(mask).cuda(),
+                                               torch.as_tensor(prev3), depth=depth, seed=8, ctr_base=100, details=True)
+    act, chosen, cand, fb = _np(act), _np(chosen), _np(cand).astype(np.uint64), _np(fb)
+    n_fb = 0
+    for i in range(n):
+        wc, wcand, wfb = O.greedy(obs[i], mask[i], prev3[i], depth)
+        bits = sum(1 << a for a in wcand)
+        assert (int(chosen[i]), int(cand[i]), bool(fb[i])) == (wc, bits, wfb), i
+        if wfb:
+            n_fb += 1
+            j = (O.philox4x32_10([100 + i, 0, 0, 1], [8, 0])[0].item() * len(wcand)) >> 32
+            assert act[i] == wcand[j]
+        else:
+            assert act[i] == wc
+    assert 0 < n_fb < n
+
+
+def test_greedy_golden_from_reference(gv1, golden):
+    g = golden("greedy")
+    for depth in (1, 2):
+        sel = g["depth"] == depth
+        act, chosen, cand, fb = gv1.greedy_actions(torch.as_tensor(g["obs"][sel]).cuda(),
+                                                   torch.as_tensor(g["mask"][sel]).cuda(),
+                                                   torch.as_tensor(g["prev3"][sel]), depth=depth, details=True)
+        assert _np(chosen).tolist() == g["chosen"][sel].tolist()
+        want_bits = [sum(1 << int(a) for a in np.flatnonzero(c)) for c in g["cand"][sel]]
+        assert [int(x) & (2**64 - 1) for x in _np(cand)] == want_bits
+        assert _np(fb).tolist() == g["fallback"][sel].tolist()
+
+
+def test_abi_rejects_bad_arguments(gv1):
+    from gobblet_rl_b200 import ops
+    v = gv1.vec_env(40)
+    buf = torch.zeros(40 * 117 + 16, dtype=torch.int8, device="cuda")
+    with pytest.raises(ops.GobbletError):
+        ops.observe(v.state, buf[1:1 + 40 * 117], v.mask, None)         # misaligned obs
+    with pytest.raises(ops.GobbletError):
+        ops.step(v.state, torch.zeros(40, dtype=torch.int64, device="cuda"), v.obs, v.mask, None, None, None, None,
+                 None, None, None, 3 << 1)                                # bad autoreset mode
+    with pytest.raises(ops.GobbletError):
+        ops.observe(v.state.cpu(), v.obs, v.mask, None)                  # no CPU path
+
+
+def test_million_env_properties(gv1):
+    """BASELINE config 3 size: invariants that need no oracle replay."""
+    n, T = 1 << 20, 48
+    a = gv1.vec_env(n, seed=0)
+    a.rollout_random(T, ring=2)
+    ep, p1, p2, steps, sumlen, illegal, both, maxlen = a.stats.tolist()
+    assert steps == n * T and illegal == 0 and ep == p1 + p2
+    assert 11.6 < sumlen / ep < 12.2 and 0.535 < p1 / ep < 0.555 and 0.005 < both / ep < 0.02
+    # determinism + sharding independence: two half-size shards with global ids == the whole
+    lo = gv1.vec_env(n // 2, seed=0, env_id_base=0)
+    hi = gv1.vec_env(n // 2, seed=0, env_id_base=n // 2)
+    lo.rollout_random(T, ring=2)
+    hi.rollout_random(T, ring=2)
+    assert torch.equal(torch.cat([lo.state, hi.state]), a.state)
+    assert (lo.stats[:7] + hi.stats[:7]).tolist() == a.stats[:7].tolist()
+    assert max(lo.stats[7].item(), hi.stats[7].item()) == maxlen
+    # the last emitted observation is the observation of the final state
+    obs_ring, mask_ring = a._rings[1], a._rings[2]
+    slot = (T - 1) % 2
+    obs, mask, _ = a.observe()
+    assert torch.equal(obs_ring[slot], obs) and torch.equal(mask_ring[slot], mask)
+    # masks are 0/1 and every env has a legal move
+    assert int(mask.max()) == 1 and int(mask.sum(1).min()) >= 1
