@@ -6,9 +6,10 @@
 
 Workload (BASELINE.json config 3, at every N so the 1->8 run is weak scaling): 2^20 lockstep envs per
 GPU, uniform random legal actions (Philox4x32-10 keyed by global env id), same-step auto-reset; one
-bench "step" = ONE launch of the fused rollout kernel = 256 lockstep env-steps of all envs, the next
-observation (117 B) and action mask (54 B) of every env written to HBM every env-step.  Outputs cycle
-through a ring of 4 step slots (717 MB > 126 MB L2), so every byte goes to DRAM.  One process per GPU;
+bench "step" = ONE launch of the fused rollout kernel = 64 lockstep env-steps of all envs, the next
+observation (117 B) and action mask (54 B) of every env written every env-step into a [64, N, ...]
+trajectory buffer (11.5 GB per launch, each byte written once per launch and far larger than the
+126 MB L2, so every emitted byte travels to HBM; a short ring would let L2 absorb the rewrites).  One process per GPU;
 envs shard by global id with no per-step communication; the only collective is the end-of-run
 all-reduce of the episode statistics (outside the timed region).
 Prints ONE JSON line (rank 0).
@@ -25,8 +26,8 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 ENVS_PER_GPU = 1 << 20
-FUSED_STEPS = 256
-RING = 4
+FUSED_STEPS = 64
+RING = FUSED_STEPS   # one trajectory slot per fused step: every emitted byte is written exactly once per launch
 BYTES_PER_ENV_STEP = 117 + 54
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
@@ -37,11 +38,12 @@ WORKLOAD = ("c3: 2^20 lockstep envs per GPU, uniform random legal actions, same-
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--fused-steps", type=int, default=FUSED_STEPS)
+    ap.add_argument("--ring", type=int, default=0, help="trajectory slots (0 = one per fused step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--plain-stores", action="store_true", help="st.global instead of st.global.cs")
@@ -189,6 +191,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     n, T = a.envs_per_gpu, a.fused_steps
+    ring = a.ring if a.ring > 0 else T
     vec = gobblet_v1.vec_env(n, device=dev, seed=0, env_id_base=rank * n, streaming_stores=not a.plain_stores)
 
     def sync_all():
@@ -198,7 +201,7 @@ def main():
             torch.cuda.synchronize(dev)
 
     for _ in range(max(3, a.warmup)):                 # >= 3 untimed warm-up steps
-        vec.rollout_random(T, ring=RING)
+        vec.rollout_random(T, ring=ring)
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = vec.kernel_launches
@@ -206,7 +209,7 @@ def main():
     t_wall0 = time.time()
     ev[0].record()
     for k in range(a.steps):
-        vec.rollout_random(T, ring=RING)
+        vec.rollout_random(T, ring=ring)
         ev[k + 1].record()
     torch.cuda.synchronize(dev)
     t_wall1 = time.time()
@@ -270,17 +273,17 @@ def main():
         if tj.get("envs") == n:
             traffic = tj["dram_bytes_per_env_step"] * n * T   # ncu --set full capture scaled to this launch
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "gbl::rollout_kernel<true,true>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "gbl::rollout_kernel<true,true,false>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
                 "launch_ms_avg": launch_ms, "launch_ms_min": per_launch[0], "launch_ms_median": per_launch[len(per_launch) // 2]}
 
     # ---- config 2 (4096 envs): latency-bound, reported beside the headline --------------------------------
     small = gobblet_v1.vec_env(4096, device=dev, seed=0)
-    small.rollout_random(512, ring=RING)
+    small.rollout_random(512, ring=4)
     torch.cuda.synchronize(dev)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    small.rollout_random(4096, ring=RING)
+    small.rollout_random(4096, ring=4)
     s1.record()
     torch.cuda.synchronize(dev)
     small_batch = {"workload": "c2: 4096 lockstep envs, 4096 fused steps, 1 launch", "value": 4096 * 4096 / (s0.elapsed_time(s1) * 1e-3),
@@ -301,8 +304,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "fused_env_steps_per_launch": T, "ring_slots": RING,
-                       "l2": f"outputs cycle through {RING * n * BYTES_PER_ENV_STEP / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "fused_env_steps_per_launch": T, "ring_slots": ring,
+                       "l2": f"each launch writes a {ring * n * BYTES_PER_ENV_STEP / 1e9:.1f} GB trajectory once (>> 126 MB L2, no flush needed)",
                        "parallelism": f"{world} independent shards by global env id, no per-step communication",
                        "stores": "st.global" if a.plain_stores else "st.global.cs"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,

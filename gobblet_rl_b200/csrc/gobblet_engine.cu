@@ -143,7 +143,8 @@ struct RolloutParams {
     uint32_t flags;
 };
 
-template <bool kFast, bool kStreaming>
+// kAux: any of rew_out / term_out / agent_out / action_log is requested (compiled out otherwise)
+template <bool kFast, bool kStreaming, bool kAux>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(RolloutParams p) {
     __shared__ __align__(16) uint32_t stage[WARPS][2][STAGE_WORDS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(RolloutParams p) {
             if (r.term && same_step) env_clear(e);
             occupancy(e, u, up);
             legal_mask(e.xo, e.yo, u, up, m0, m1);
-            if (valid) {
+            if (kAux && valid) {
                 const int64_t o = (int64_t)slot * p.n + g;
                 if (p.rew_out) *reinterpret_cast<char2 *>(p.rew_out + 2 * o) = make_char2((signed char)r.r1, (signed char)r.r2);
                 if (p.term_out) p.term_out[o] = r.term;
@@ -344,13 +345,20 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     const bool plain = flags & GBL_STORE_DEFAULT_POLICY;
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = grid_for(n);
+    const bool aux = rew_out || term_out || agent_out || action_log;
+#define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
+    do {                                                                            \
+        if (aux) rollout_kernel<F, S, true><<<grid, BLOCK, 0, s>>>(p);              \
+        else rollout_kernel<F, S, false><<<grid, BLOCK, 0, s>>>(p);                 \
+    } while (0)
     if (fast) {
-        if (plain) rollout_kernel<true, false><<<grid, BLOCK, 0, s>>>(p);
-        else rollout_kernel<true, true><<<grid, BLOCK, 0, s>>>(p);
+        if (plain) GBL_LAUNCH_ROLLOUT(true, false);
+        else GBL_LAUNCH_ROLLOUT(true, true);
     } else {
-        if (plain) rollout_kernel<false, false><<<grid, BLOCK, 0, s>>>(p);
-        else rollout_kernel<false, true><<<grid, BLOCK, 0, s>>>(p);
+        if (plain) GBL_LAUNCH_ROLLOUT(false, false);
+        else GBL_LAUNCH_ROLLOUT(false, true);
     }
+#undef GBL_LAUNCH_ROLLOUT
     return check_launch("gbl_rollout_random");
 }
 

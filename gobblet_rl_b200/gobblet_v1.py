@@ -63,6 +63,7 @@ class raw_env(AECEnv):
         super().__init__()
         # one env of the batched engine; illegal moves pass the turn like the reference's raw_env
         self._vec = VecEnv(1, device=device, illegal_mode="pass", autoreset="off")
+        self._scratch = None
         self.board = _BoardView(self)
         self.board_size = 3
         self.agents = ["player_1", "player_2"]
@@ -100,14 +101,27 @@ class raw_env(AECEnv):
         self._sel = int(packed[174])
 
     def observe(self, agent):                                   # gobblet.py:179-215
-        selected = self.possible_agents[self._sel]
-        if agent == selected:
-            return {"observation": self._obs.copy(), "action_mask": self._mask.copy()}
-        # the other agent: planes from its own perspective (sign flip only, gobblet.py:182-185) and an
-        # all-zero mask (gobblet.py:209-213)
-        o = np.empty_like(self._obs)
-        o[..., 0:6], o[..., 6:12], o[..., 12] = self._obs[..., 6:12], self._obs[..., 0:6], 1 - self._obs[..., 12]
-        return {"observation": o, "action_mask": np.zeros(54, "int8")}
+        # the reference indexes the LIVE agent list (gobblet.py:182, :199, :225): once a dead step has
+        # removed player_1, player_2 is observed (and its mask built) as index 0
+        idx = self.agents.index(agent)
+        if idx == self._sel:
+            planes = self._obs.copy()
+        else:   # the other agent's perspective: sign flip only (gobblet.py:182-185) = own/opponent planes swapped
+            planes = np.empty_like(self._obs)
+            planes[..., 0:6], planes[..., 6:12] = self._obs[..., 6:12], self._obs[..., 0:6]
+            planes[..., 12] = 1 - self._obs[..., 12]
+        if agent != self.agent_selection:                       # all-zero mask (gobblet.py:209-213)
+            return {"observation": planes, "action_mask": np.zeros(54, "int8")}
+        if idx == self._sel:
+            return {"observation": planes, "action_mask": self._mask.copy()}
+        # agent_selection moved on without a board move (dead steps after the game ended): the reference
+        # still builds a live mask for it (gobblet.py:209, :223-228).  Evaluate the same board with that
+        # agent to move on a scratch env of the engine.
+        if self._scratch is None:
+            self._scratch = VecEnv(1, device=self._vec.device, illegal_mode="pass", autoreset="off")
+        sq, _ = self._vec.squares()
+        _, mask, _ = self._scratch.set_squares(sq, torch.tensor([idx], dtype=torch.uint8))
+        return {"observation": planes, "action_mask": mask[0].cpu().numpy().copy()}
 
     def observation_space(self, agent):
         return self.observation_spaces[agent]
