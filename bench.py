@@ -174,12 +174,30 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ---------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit_line(obj):
+    """The contract is ONE JSON line on stdout: everything else a library prints (e.g. NCCL's version
+    banner) is diverted to stderr by main(); the line goes to the original stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                     # stray prints (NCCL banner, warnings) -> stderr
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -311,7 +329,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "small_batch": small_batch,
             "episode_stats": dict(zip(("episodes", "p1_wins", "p2_wins", "steps", "sum_len", "illegal", "both_lines", "max_len"), stats.tolist()))}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
