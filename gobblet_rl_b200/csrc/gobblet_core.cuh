@@ -215,6 +215,11 @@ __device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1,
                                                uint32_t flags, Stats &st) {
     StepResult r = {0, 0, false, false, true};
     const uint32_t autoreset = (flags >> 1) & 3u;
+    if (!kFast && (flags & 0x10u) && action == 255u) {   // GBL_ACTION_SKIP_255: env not in the stepped subset
+        r.acted = false;
+        r.term = e.done != 0; r.trunc = e.trunc != 0;
+        return r;
+    }
     if (!kFast && e.done) {
         r.acted = false;
         if (autoreset == 2u) env_clear(e);          // next_step: this call only resets

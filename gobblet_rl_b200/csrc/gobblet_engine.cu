@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(StepParams p) {
         occupancy(e, u, up);
         legal_mask(e.xo, e.yo, u, up, m0, m1);
         const bool same_step = (p.flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_SAME_STEP;
+        if (same_step && !r.acted) r.term = false;     // skipped env: nothing to reset
         if (same_step) {
             if (p.final_obs && p.final_mask) {      // terminal observation before it is replaced
                 stage_bits(stage[warp][1], cfg, lane, e.s, m0, m1);

@@ -16,14 +16,16 @@ OBS_BYTES, MASK_BYTES, STATE_BYTES, NUM_ACTIONS = 117, 54, 16, 54
 ILLEGAL_TERMINATE, ILLEGAL_PASS = 0x0, 0x1
 AUTORESET_OFF, AUTORESET_SAME_STEP, AUTORESET_NEXT_STEP = 0 << 1, 1 << 1, 2 << 1
 STORE_DEFAULT_POLICY = 0x8
+ACTION_SKIP_255 = 0x10
 ABI_VERSION = 1
 
 _ILLEGAL = {"terminate": ILLEGAL_TERMINATE, "pass": ILLEGAL_PASS}
 _AUTORESET = {"off": AUTORESET_OFF, "same_step": AUTORESET_SAME_STEP, "next_step": AUTORESET_NEXT_STEP}
 
 
-def make_flags(illegal_mode="terminate", autoreset="same_step", streaming_stores=True):
-    return _ILLEGAL[illegal_mode] | _AUTORESET[autoreset] | (0 if streaming_stores else STORE_DEFAULT_POLICY)
+def make_flags(illegal_mode="terminate", autoreset="same_step", streaming_stores=True, skip255=False):
+    return (_ILLEGAL[illegal_mode] | _AUTORESET[autoreset] | (0 if streaming_stores else STORE_DEFAULT_POLICY)
+            | (ACTION_SKIP_255 if skip255 else 0))
 
 
 def _load():
@@ -143,9 +145,12 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
         so, sm = obs_out.stride(0), mask_out.stride(0)          # int8 => element stride == bytes
         if obs_out[0].numel() != n * OBS_BYTES or not obs_out[0].is_contiguous() or not mask_out[0].is_contiguous():
             raise GobbletError("each ring slot must be a contiguous [n,3,3,13] / [n,54] int8 block")
-    for t in (rew_out, term_out, agent_out):
-        if t is not None and t.shape[0] != ring:
-            raise GobbletError("per-step outputs must share the ring length of obs_out")
+    aux = [t for t in (rew_out, term_out, agent_out) if t is not None]
+    if obs_out is None and aux:
+        ring = aux[0].shape[0]
+    for t in aux:
+        if t.shape[0] != ring:
+            raise GobbletError("per-step outputs must share one ring length (that of obs_out when it is given)")
     with torch.cuda.device(dev):
         _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(obs_out),
                                       _ptr(mask_out), so, sm, ring, _ptr(rew_out), _ptr(term_out), _ptr(agent_out),

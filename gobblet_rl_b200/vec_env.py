@@ -29,14 +29,15 @@ class VecEnv:
     """
 
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, illegal_mode: str = "terminate",
-                 autoreset: str = "same_step", env_id_base: int = 0, streaming_stores: bool = True):
+                 autoreset: str = "same_step", env_id_base: int = 0, streaming_stores: bool = True,
+                 skip255: bool = False):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ops.GobbletError("VecEnv needs a CUDA device: the engine has no CPU path")
         self.seed, self.env_id_base = int(seed), int(env_id_base)
         self.illegal_mode, self.autoreset = illegal_mode, autoreset
-        self.flags = ops.make_flags(illegal_mode, autoreset, streaming_stores)
+        self.flags = ops.make_flags(illegal_mode, autoreset, streaming_stores, skip255)
         n, dev = self.num_envs, self.device
         self.state = torch.zeros((n, 2), dtype=torch.int64, device=dev)
         self.obs = torch.zeros((n, 3, 3, 13), dtype=torch.int8, device=dev)
@@ -70,20 +71,26 @@ class VecEnv:
         self.kernel_launches += 1
         return self.obs, self.mask, self.agent_id
 
-    def step(self, actions: torch.Tensor, final: Optional[tuple] = None, out: Optional[tuple] = None):
+    def step(self, actions: torch.Tensor, final: Optional[tuple] = None, out: Optional[tuple] = None,
+             aux_out: Optional[tuple] = None):
         """-> (obs[N,3,3,13] i8, mask[N,54] i8, rew[N,2] i8, terminated[N] bool, truncated[N] bool, agent_id[N] u8)
 
-        `final=(final_obs, final_mask)` receives the observation before a same-step reset replaces it."""
+        `final=(final_obs, final_mask)` receives the observation before a same-step reset replaces it.
+        `out=(obs, mask)` and `aux_out=(rew, terminated, truncated, agent_id)` redirect the kernel's stores,
+        e.g. straight into the slot of a trajectory / replay buffer (no copy).
+        With `illegal_mode="terminate"` the observation after an illegal move is the MOVER's (live mask);
+        PettingZoo's `last()` would select player_1 there -- `adapters.PettingZooVecEnv` applies that rule."""
         actions = torch.as_tensor(actions, device=self.device)
         if actions.dtype not in (torch.uint8, torch.int32, torch.int64):
             actions = actions.to(torch.int64)
         obs, mask = (self.obs, self.mask) if out is None else out
+        rew, term, trunc, agent = (self.rew, self.terminated, self.truncated, self.agent_id) if aux_out is None else aux_out
         fobs, fmask = (None, None) if final is None else final
-        ops.step(self.state, actions.contiguous(), obs, mask, self.rew, self.terminated.view(torch.uint8),
-                 self.truncated.view(torch.uint8), self.agent_id, fobs, fmask, self.stats, self.flags)
+        ops.step(self.state, actions.contiguous(), obs, mask, rew, term.view(torch.uint8), trunc.view(torch.uint8),
+                 agent, fobs, fmask, self.stats, self.flags)
         self.step_count += 1
         self.kernel_launches += 1
-        return obs, mask, self.rew, self.terminated, self.truncated, self.agent_id
+        return obs, mask, rew, term, trunc, agent
 
     def rollout_random(self, T: int, ring: int = 1, emit: bool = True, per_step: bool = False,
                        log_actions: bool = False):

@@ -26,8 +26,11 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def flags(illegal_mode="terminate", autoreset="same_step"):
-    return (ILLEGAL_PASS if illegal_mode == "pass" else 0) | AUTORESET[autoreset]
+ACTION_SKIP_255 = 0x10
+
+
+def flags(illegal_mode="terminate", autoreset="same_step", skip255=False):
+    return (ILLEGAL_PASS if illegal_mode == "pass" else 0) | AUTORESET[autoreset] | (ACTION_SKIP_255 if skip255 else 0)
 
 
 # ---- Board-level -------------------------------------------------------------------------------
@@ -57,9 +60,9 @@ def observe(squares, agent, selected):
 
 # ---- vectorised env mirroring the engine's C ABI ---------------------------------------------
 class VecOracle:
-    def __init__(self, n, illegal_mode="terminate", autoreset="same_step"):
+    def __init__(self, n, illegal_mode="terminate", autoreset="same_step", skip255=False):
         self.n = int(n)
-        self.flags = flags(illegal_mode, autoreset)
+        self.flags = flags(illegal_mode, autoreset, skip255)
         self._buf = np.zeros(self.n * lib().gbo_env_sizeof(), np.uint8)
         self.stats = np.zeros(8, np.int64)
         lib().gbo_vec_reset(_p(self._buf), C.c_int64(self.n))
