@@ -4,8 +4,8 @@
     raw_env(render_mode=None, args=None)   PettingZoo AEC env (gobblet.py:123-290), a batch-of-1 view
     GreedyGobbletPolicy(depth=2, seed=0)   greedy_policy.py:8-221
     vec_env(num_envs, ...)                 NEW: vectorised entry point over torch CUDA tensors
-Rendering (pygame / text, gobblet.py:292-573) is out of scope; `render()` only warns, as the reference
-does for render_mode=None (gobblet.py:293-297).
+pygame rendering (gobblet.py:430-573) is out of scope; the `text` / `text_full` debug views are provided
+(`text_view.py`); with render_mode=None `render()` only warns, as the reference does (gobblet.py:293-297).
 """
 import warnings
 
@@ -45,6 +45,11 @@ class _BoardView:
     def squares(self):
         sq, _ = self._owner._vec.squares()
         return sq[0].cpu().numpy().astype(np.float64)
+
+    def get_flatboard(self):
+        """Top-of-stack view (board.py:159-177) of the engine state; formatting only."""
+        from .text_view import flatboard_from_squares
+        return flatboard_from_squares(self.squares)
 
     def __str__(self):
         return str(self.squares.reshape(3, 3, 3))
@@ -169,7 +174,13 @@ class raw_env(AECEnv):
         if self.render_mode is None:
             warnings.warn("You are calling render method without specifying any render mode.")
             return
-        raise NotImplementedError("pygame / text rendering is out of scope of the B200 engine (SURVEY.md section 2 #3)")
+        if self.render_mode in ("text", "text_full"):           # debug views, gobblet.py:316-429
+            from .text_view import render_text
+            print(render_text(self.board.squares, self.turn, self.agent_selection, self.action,
+                              full=self.render_mode == "text_full"), end="")
+            return
+        raise NotImplementedError("pygame rendering (human / rgb_array) is out of scope of the B200 engine "
+                                  "(SURVEY.md section 2 #3)")
 
     def close(self):
         self.screen = None

@@ -17,6 +17,7 @@ Fixtures
                       same with illegal actions injected ("pass" semantics, board.py:125-126).
   env_wrapped.npz     env() (wrapper stack, gobblet.py:110-117, stand-in wrappers): full agent_iter
                       loops incl. dead steps and illegal-move termination: the last() 5-tuples.
+  render_text.npz     stdout of render_mode="text" / "text_full" along one game (debug views, gobblet.py:299-429).
   greedy.npz          GreedyGobbletPolicy(depth 1 and 2).compute_action on sampled positions with
                       np.random.choice patched to expose (chosen-before-fallback, candidates).
 """
@@ -228,6 +229,26 @@ def greedy_cases(Board, gp_mod, n_pos, rng):
     return out
 
 
+def render_text_cases(gob):
+    """stdout of the reference's text / text_full renderers (gobblet.py:299-429) along one game."""
+    import contextlib
+    import io
+    out = {}
+    actions = [18, 36, 28, 46, 2, 40, 13, 47, 26]
+    out["actions"] = np.array(actions, np.int64)
+    for mode in ("text", "text_full"):
+        env = gob.raw_env(render_mode=mode)
+        env.reset()
+        chunks = []
+        for a in actions:
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                env.step(a)
+            chunks.append(buf.getvalue())
+        out[mode] = np.array(chunks)
+    return out
+
+
 def main():
     root = RL.find_reference_root()
     assert root, "reference not found"
@@ -242,6 +263,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "env_traces_illegal.npz"), **raw_env_traces(gob, 40, rng, 0.2))
     np.savez_compressed(os.path.join(OUT, "env_wrapped.npz"), **wrapped_env_traces(gob, 40, rng, 0.04))
     np.savez_compressed(os.path.join(OUT, "greedy.npz"), **greedy_cases(Board, gp, 480, rng))
+    np.savez_compressed(os.path.join(OUT, "render_text.npz"), **render_text_cases(gob))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
