@@ -1,11 +1,11 @@
 // gobblet_core.cuh -- register-resident bitboard engine for 3x3 Gobblet Gobblers (sm_100a).
 //
-// One environment per thread.  The per-env state is kept MOVER-RELATIVE:
+// One environment per thread.  The per-env state is kept MOVER-RELATIVE in four registers:
 //   xo, yo : 27-bit boards of the mover's odd / even pieces (pieces 1,3,5 / 2,4,6), bit 9*level+pos
 //            -- the reference's `squares` index (gobblet_rl/game/board.py:33, :76-79)
 //   xp, yp : same for the opponent
-//   s[4]   : the 117-bit observation bitmap the mover would see, bit pos*13+c  (gobblet.py:188-208)
-// Everything below is integer bit arithmetic; nothing is a contraction, so no tensor cores.
+// so handing over the turn is a register swap.  Everything below is integer bit arithmetic; nothing is
+// a contraction, so no tensor cores.
 #pragma once
 #include <stdint.h>
 
@@ -13,34 +13,8 @@ namespace gbl {
 
 constexpr uint32_t F0 = 0x000001FFu, F1 = 0x0003FE00u, F2 = 0x07FC0000u, B27 = 0x07FFFFFFu;
 
-// ---- 128-bit constants of the observation bitmap -------------------------------------------
-constexpr uint32_t obs_mask_word(int word, int c_lo, int c_hi) {
-    uint32_t m = 0;
-    for (int p = 0; p < 9; ++p)
-        for (int c = c_lo; c <= c_hi; ++c) {
-            int b = 13 * p + c;
-            if ((b >> 5) == word) m |= 1u << (b & 31);
-        }
-    return m;
-}
-constexpr uint32_t OWN_0 = obs_mask_word(0, 0, 5), OWN_1 = obs_mask_word(1, 0, 5), OWN_2 = obs_mask_word(2, 0, 5), OWN_3 = obs_mask_word(3, 0, 5);
-constexpr uint32_t OPP_0 = obs_mask_word(0, 6, 11), OPP_1 = obs_mask_word(1, 6, 11), OPP_2 = obs_mask_word(2, 6, 11), OPP_3 = obs_mask_word(3, 6, 11);
-constexpr uint32_t P12_0 = obs_mask_word(0, 12, 12), P12_1 = obs_mask_word(1, 12, 12), P12_2 = obs_mask_word(2, 12, 12), P12_3 = obs_mask_word(3, 12, 12);
-
-// PTX shifts clamp the amount at 32 (result 0), unlike C++ where >= 32 is undefined.
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
-#ifdef __CUDA_ARCH__
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
-    return r;
-#else  // host-side emulation used only by tests/emul (never by the product)
-    return s >= 32u ? 0u : v << s;
-#endif
-}
-
 struct Env {
     uint32_t xo, yo, xp, yp;  // mover-relative boards
-    uint32_t s[4];            // mover-relative observation bitmap
     uint32_t agent;           // agent_selection: 0 = player_1 (gobblet.py:160-161)
     uint32_t plies;           // raw_env.turn (gobblet.py:270)
     uint32_t done, trunc;     // terminations / truncations (gobblet.py:263; wrapper :114)
@@ -52,34 +26,18 @@ struct Stats {
 
 __device__ __forceinline__ void env_clear(Env &e) {  // raw_env.reset, gobblet.py:275-290
     e.xo = e.yo = e.xp = e.yp = 0;
-    e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0;
     e.agent = 0; e.plies = 0; e.done = 0; e.trunc = 0;
 }
 
-// set bit b of the 117-bit bitmap; negative b is a no-op (clamped shifts)
-__device__ __forceinline__ void s_or_bit(uint32_t (&s)[4], int b) {
-    uint32_t ub = (uint32_t)b;
-    s[0] |= shl_clamp(1u, ub);
-    s[1] |= shl_clamp(1u, ub - 32u);
-    s[2] |= shl_clamp(1u, ub - 64u);
-    s[3] |= shl_clamp(1u, ub - 96u);
-}
-
-// observation bitmap from the boards: plane c (piece c+1) of the mover at 0..5, opponent 6..11,
-// plane 12 = mover is player_2 (gobblet.py:188-206)
-__device__ __forceinline__ void rebuild_obs_bits(Env &e) {
-    e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0;
-    const uint32_t w[4] = {e.xo, e.yo, e.xp, e.yp};
-    const int cbase[4] = {0, 1, 6, 7};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-            uint32_t field = (w[i] >> (9 * f)) & 0x1FFu;
-            int pos = __ffs(field) - 1;  // -1 when the piece is not on the board
-            s_or_bit(e.s, 13 * pos + cbase[i] + 2 * f);
-        }
-    if (e.agent) { e.s[0] |= P12_0; e.s[1] |= P12_1; e.s[2] |= P12_2; e.s[3] |= P12_3; }
+// index of the most significant set bit, 0xFFFFFFFF for 0 (one FLO instruction)
+__device__ __forceinline__ uint32_t bfind(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+#else  // host-side emulation used only by tests/emul (never by the product)
+    return v ? 31u - (uint32_t)__builtin_clz(v) : 0xFFFFFFFFu;
+#endif
 }
 
 // ---- HBM state (16 B / env, absolute player_1 / player_2 layout, see include/gobblet_b200.h) ----
@@ -90,7 +48,6 @@ __device__ __forceinline__ void env_unpack(Env &e, ulonglong2 v) {
     e.agent = meta & 1u; e.done = (meta >> 1) & 1u; e.trunc = (meta >> 2) & 1u; e.plies = meta >> 3;
     if (e.agent == 0) { e.xo = x1; e.yo = y1; e.xp = x2; e.yp = y2; }
     else              { e.xo = x2; e.yo = y2; e.xp = x1; e.yp = y1; }
-    rebuild_obs_bits(e);
 }
 
 __device__ __forceinline__ ulonglong2 env_pack(const Env &e) {
@@ -164,52 +121,34 @@ __device__ __forceinline__ int winner_rel(uint32_t to, uint32_t tp, bool &both) 
     return (lo > lp) - (lp > lo);
 }
 
-// Board.play_turn for a LEGAL action of the mover (board.py:118-132) + bitmap update.
+// Board.play_turn for a LEGAL action of the mover (board.py:118-132)
 __device__ __forceinline__ void apply_move(Env &e, uint32_t action) {
     uint32_t k = (action * 57u) >> 9;   // piece-1 = action // 9   (board.py:67-68), exact for 0..53
     uint32_t pos = action - 9u * k;     // action % 9              (board.py:63-64)
     uint32_t f9 = 9u * (k >> 1);        // level offset            (board.py:71-79)
     uint32_t field = 0x1FFu << f9, bit = 1u << (f9 + pos);
-    bool is_y = k & 1u;
-    uint32_t cur = is_y ? e.yo : e.xo;
-    uint32_t old = cur & field;         // previous location, if placed (board.py:128-130)
-    cur = (cur & ~field) | bit;
-    if (is_y) e.yo = cur; else e.xo = cur;
-    int b_old = 13 * (__ffs(old) - 1 - (int)f9) + (int)k;  // negative when the piece was in hand
-    uint32_t b_new = 13u * pos + k;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        e.s[j] = (e.s[j] & ~shl_clamp(1u, (uint32_t)b_old - 32u * j)) | shl_clamp(1u, b_new - 32u * j);
+    if (k & 1u) e.yo = (e.yo & ~field) | bit;   // clear the previous location, if placed (:128-130)
+    else        e.xo = (e.xo & ~field) | bit;
 }
 
-// hand the turn to the other player: swap the piece sets, swap the own/opponent halves of every
-// 13-bit square field, set plane 12 for player_2 (gobblet.py:182-185, :199-206, :246, :267)
+// hand the turn to the other player (gobblet.py:246, :267): the views are mover-relative
 __device__ __forceinline__ void pass_turn(Env &e) {
     uint32_t t;
     t = e.xo; e.xo = e.xp; e.xp = t;
     t = e.yo; e.yo = e.yp; e.yp = t;
     e.agent ^= 1u;
-    const uint32_t a = e.agent ? 0xFFFFFFFFu : 0u;
-    const uint32_t s0 = e.s[0], s1 = e.s[1], s2 = e.s[2], s3 = e.s[3];
-    const uint32_t l0 = s0 << 6, l1 = __funnelshift_l(s0, s1, 6), l2 = __funnelshift_l(s1, s2, 6),
-                   l3 = __funnelshift_l(s2, s3, 6);
-    const uint32_t r0 = __funnelshift_r(s0, s1, 6), r1 = __funnelshift_r(s1, s2, 6),
-                   r2 = __funnelshift_r(s2, s3, 6), r3 = s3 >> 6;
-    e.s[0] = (l0 & OPP_0) | (r0 & OWN_0) | (a & P12_0);
-    e.s[1] = (l1 & OPP_1) | (r1 & OWN_1) | (a & P12_1);
-    e.s[2] = (l2 & OPP_2) | (r2 & OWN_2) | (a & P12_2);
-    e.s[3] = (l3 & OPP_3) | (r3 & OWN_3) | (a & P12_3);
 }
 
 // ---- one env.step (gobblet.py:231-273 + wrapper :110-117) -----------------------------------------
 struct StepResult {
     int r1, r2;       // env.rewards[player_1], [player_2]
     bool term, trunc; // flags of THIS step
-    bool acted;       // an action was consumed (false for dead envs / reset-only steps)
+    bool acted;       // an action was consumed (false for dead envs / reset-only / skipped steps)
 };
 
 // (m0, m1) = legal mask of the mover BEFORE the move.  kFast drops the paths a random-legal rollout
-// with same-step auto-reset can never take (dead env, illegal action).
+// with same-step auto-reset can never take (dead env, illegal action, skipped env) and leaves the
+// statistics that follow arithmetically from the step count (steps, sumlen, p2w, illegal) to the caller.
 template <bool kFast>
 __device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1, uint32_t action,
                                                uint32_t flags, Stats &st) {
@@ -226,7 +165,7 @@ __device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1,
         else { r.term = true; r.trunc = e.trunc != 0; }
         return r;
     }
-    st.steps++;
+    if (!kFast) st.steps++;
     const uint32_t mover = e.agent;
     bool legal = true;
     if (!kFast) {
@@ -252,15 +191,16 @@ __device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1,
     }
     pass_turn(e);
     e.plies++;
-    if (w != 0) {                                   // gobblet.py:248-263
-        const uint32_t winner = w > 0 ? mover : mover ^ 1u;
-        r.r1 = winner == 0 ? 1 : -1;
-        r.r2 = -r.r1;
-        r.term = true;
-        e.done = 1;
-        st.episodes++; st.p1w += winner == 0; st.p2w += winner == 1;
-        st.sumlen += e.plies; st.both += both; st.maxlen = max(st.maxlen, e.plies);
-    }
+    // gobblet.py:248-263, branch-free: the winner is the mover when w > 0, the other player when w < 0
+    const bool over = w != 0;
+    const bool p1_won = over && ((w > 0) == (mover == 0));
+    r.term = over;
+    r.r1 = over ? (p1_won ? 1 : -1) : 0;
+    r.r2 = -r.r1;
+    e.done = over;
+    st.episodes += over; st.p1w += p1_won; st.both += both;
+    st.maxlen = max(st.maxlen, over ? e.plies : 0u);
+    if (!kFast) { st.p2w += over && !p1_won; st.sumlen += over ? e.plies : 0u; }
     return r;
 }
 
@@ -308,24 +248,29 @@ __device__ __forceinline__ uint32_t sample_action(uint32_t m0, uint32_t m1, uint
     return cnt ? select_bit(m0, m1, __umulhi(draw, cnt)) : 0u;
 }
 
-// ---- emission: per-env bitmaps -> coalesced int8 tensors ---------------------------------------------
+// ---- emission: per-env boards -> coalesced int8 tensors ----------------------------------------------
 // A warp owns 32 consecutive envs => 32*117 = 3744 contiguous observation bytes and 32*54 = 1728
-// contiguous mask bytes (both multiples of 16).  Each lane shifts its 117-bit / 54-bit bitmap to its
-// bit offset in the warp's packed stream, the boundary words are merged with one shuffle, the
-// stream is staged in shared memory (171 words), and every lane then turns 16 stream bits into 16
-// bytes (nibble * 0x00204081 & 0x01010101) and issues one fully coalesced 128-bit store.
-constexpr int OBS_WORDS = 117, MASK_WORDS = 54, STAGE_WORDS = 176;  // 171 used, padded to 16 B
-constexpr int OBS_VEC = 234, MASK_VEC = 108;                        // uint4 stores per warp
+// contiguous mask bytes (both multiples of 16), staged per warp in shared memory:
+//   * observation: the image is the FINAL byte layout (byte lane*117 + pos*13 + c, gobblet.py:188-208).
+//     It is kept all-zero between steps; each lane SCATTERS the <= 12 one-bytes of its pieces (one FLO
+//     + one IMAD + one predicated STS.U8 per piece) and, for player_2, the 9 bytes of plane 12; the
+//     warp then copies the image out with 128-bit loads / stores, zeroing it behind itself.
+//   * mask: each lane shifts its 54-bit mask to its bit offset in the warp's packed stream (boundary
+//     words merged with one shuffle); every lane then turns 16 stream bits into 16 bytes
+//     (nibble * 0x00204081 & 0x01010101).
+// Every global store is a full 128-bit, fully coalesced STG: 234 + 108 per warp and step.
+constexpr int OBS_IMG_BYTES = 32 * 117, MASK_WORDS = 54;
+constexpr int STAGE_BYTES = OBS_IMG_BYTES + 4 * MASK_WORDS + 8;  // 3968, multiple of 16
+constexpr int OBS_VEC = 234, MASK_VEC = 108;                    // uint4 stores per warp
 
 struct LaneCfg {
-    uint32_t ofo, oso, mfo, mso;
-    bool on4, mn2;
+    uint32_t mfo, mso;
+    bool mn2;
 };
 
 __device__ __forceinline__ LaneCfg make_lane_cfg(uint32_t lane) {
     LaneCfg c;
-    uint32_t o = 117u * lane, o2 = o + 117u, m = 54u * lane, m2 = m + 54u;
-    c.ofo = o >> 5; c.oso = o & 31u; c.on4 = ((o2 >> 5) - c.ofo) == 4u;
+    uint32_t m = 54u * lane, m2 = m + 54u;
     c.mfo = m >> 5; c.mso = m & 31u; c.mn2 = ((m2 >> 5) - c.mfo) == 2u;
     return c;
 }
@@ -346,61 +291,98 @@ __device__ __forceinline__ void store16(int8_t *p, uint4 v) {
     else *reinterpret_cast<uint4 *>(p) = v;
 }
 
-// stage: all 32 lanes of the warp must call (shuffle inside).  stage_buf = this warp's STAGE_WORDS.
-__device__ __forceinline__ void stage_bits(uint32_t *stage_buf, const LaneCfg &c, uint32_t lane,
-                                           const uint32_t (&s)[4], uint32_t m0, uint32_t m1) {
-    const uint32_t w0 = s[0] << c.oso, w1 = __funnelshift_l(s[0], s[1], c.oso),
-                   w2 = __funnelshift_l(s[1], s[2], c.oso), w3 = __funnelshift_l(s[2], s[3], c.oso),
-                   w4 = __funnelshift_l(s[3], 0u, c.oso);
-    uint32_t tail = c.on4 ? w4 : w3;            // partial word shared with the next lane
-    uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
-    if (lane == 0) prev = 0;
-    stage_buf[c.ofo] = w0 | prev;
-    stage_buf[c.ofo + 1] = w1;
-    stage_buf[c.ofo + 2] = w2;
-    if (c.on4) stage_buf[c.ofo + 3] = w3;
-    const uint32_t v0 = m0 << c.mso, v1 = __funnelshift_l(m0, m1, c.mso), v2 = __funnelshift_l(m1, 0u, c.mso);
-    tail = c.mn2 ? v2 : v1;
-    prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
-    if (lane == 0) prev = 0;
-    stage_buf[OBS_WORDS + c.mfo] = v0 | prev;
-    if (c.mn2) stage_buf[OBS_WORDS + c.mfo + 1] = v1;
+// zero the observation image once per kernel (every emit_chunk leaves it zeroed again)
+__device__ __forceinline__ void stage_init(uint8_t *stage, uint32_t lane) {
+    uint4 *img = reinterpret_cast<uint4 *>(stage);
+    for (uint32_t q = lane; q < OBS_VEC; q += 32u) img[q] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this warp
-// that exist (32 except in the last warp).
+// store the byte 1 at shared-memory offset `off` of `base` iff cond != 0, as ONE predicated STS.U8
+// (a C++ `if` around the store compiles to a divergent branch with BSSY/BSYNC per piece)
+__device__ __forceinline__ void store_one_if(uint8_t *base, uint32_t off, uint32_t cond) {
+#ifdef __CUDA_ARCH__
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(base) + off;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}"
+                 :: "r"(cond), "r"(addr), "r"(1u) : "memory");
+#else  // host-side emulation used only by tests/emul (never by the product)
+    if (cond) base[off] = 1;
+#endif
+}
+
+// one byte per piece on the board: plane c of the mover's piece c+1 at 0..5, opponent 6..11
+__device__ __forceinline__ void scatter_pieces(uint8_t *mine, uint32_t w, int plane0) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        const uint32_t fld = w & (0x1FFu << (9 * f));                                  // one-hot or empty
+        store_one_if(mine, 13u * bfind(fld) + (uint32_t)(plane0 + 2 * f - 117 * f), fld);   // pos = bfind - 9f
+    }
+}
+
+// stage: all 32 lanes of the warp must call (shuffle inside).  stage = this warp's STAGE_BYTES.
+// The caller puts a __syncwarp() between stage_env and emit_chunk and one after emit_chunk.
+__device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint32_t lane, const Env &e,
+                                          uint32_t m0, uint32_t m1) {
+    uint8_t *mine = stage + 117u * lane;
+    scatter_pieces(mine, e.xo, 0);
+    scatter_pieces(mine, e.yo, 1);
+    scatter_pieces(mine, e.xp, 6);
+    scatter_pieces(mine, e.yp, 7);
+    if (e.agent) {                                      // plane 12: the viewer is player_2 (gobblet.py:199-206)
+#pragma unroll
+        for (int p = 0; p < 9; ++p) mine[13 * p + 12] = 1;
+    }
+    uint32_t *mbits = reinterpret_cast<uint32_t *>(stage + OBS_IMG_BYTES);
+    const uint32_t v0 = m0 << c.mso, v1 = __funnelshift_l(m0, m1, c.mso), v2 = __funnelshift_l(m1, 0u, c.mso);
+    uint32_t tail = c.mn2 ? v2 : v1;                    // partial word shared with the next lane
+    uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+    if (lane == 0) prev = 0;
+    mbits[c.mfo] = v0 | prev;
+    if (c.mn2) mbits[c.mfo + 1] = v1;
+}
+
+// copy / expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this
+// warp that exist (32 except in the last warp).
 template <bool kStreaming>
-__device__ __forceinline__ void emit_chunk(const uint32_t *stage_buf, uint32_t lane, int8_t *obs_chunk,
+__device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t *obs_chunk,
                                            int8_t *mask_chunk, int nvalid) {
-    const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage_buf);
+    uint4 *img = reinterpret_cast<uint4 *>(stage);
+    const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage + OBS_IMG_BYTES);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid == 32) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             uint32_t q = lane + 32u * i;
-            if (i < 7 || q < OBS_VEC) store16<kStreaming>(obs_chunk + 16u * q, expand16(hb[q]));
+            if (i < 7 || q < OBS_VEC) {
+                uint4 v = img[q];
+                img[q] = zero;
+                store16<kStreaming>(obs_chunk + 16u * q, v);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint32_t q = lane + 32u * i;
-            if (i < 3 || q < MASK_VEC) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[2 * OBS_WORDS + q]));
+            if (i < 3 || q < MASK_VEC) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
         }
     } else {  // ragged last warp: vector stores while fully inside, bytes at the edge
         const uint32_t ob = 117u * nvalid, mb = 54u * nvalid;
         for (uint32_t q = lane; q < OBS_VEC; q += 32u) {
-            uint4 v = expand16(hb[q]);
+            uint4 v = img[q];
+            img[q] = zero;
             if (16u * q + 16u <= ob) store16<kStreaming>(obs_chunk + 16u * q, v);
-            else {
-                const int8_t *b = reinterpret_cast<const int8_t *>(&v);
-                for (uint32_t j = 0; j < 16u && 16u * q + j < ob; ++j) obs_chunk[16u * q + j] = b[j];
-            }
+            else
+                for (uint32_t j = 0; j < 16u && 16u * q + j < ob; ++j) {
+                    uint32_t w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
+                    obs_chunk[16u * q + j] = (int8_t)(w >> (8u * (j & 3u)));
+                }
         }
         for (uint32_t q = lane; q < MASK_VEC; q += 32u) {
-            uint4 v = expand16(hb[2 * OBS_WORDS + q]);
+            uint4 v = expand16(hb[q]);
             if (16u * q + 16u <= mb) store16<kStreaming>(mask_chunk + 16u * q, v);
-            else {
-                const int8_t *b = reinterpret_cast<const int8_t *>(&v);
-                for (uint32_t j = 0; j < 16u && 16u * q + j < mb; ++j) mask_chunk[16u * q + j] = b[j];
-            }
+            else
+                for (uint32_t j = 0; j < 16u && 16u * q + j < mb; ++j) {
+                    uint32_t w = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
+                    mask_chunk[16u * q + j] = (int8_t)(w >> (8u * (j & 3u)));
+                }
         }
     }
 }

@@ -45,19 +45,21 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(ulonglong2 *state, const u
 template <bool kStreaming>
 __global__ void __launch_bounds__(BLOCK)
 observe_kernel(const ulonglong2 *__restrict__ state, int8_t *obs, int8_t *mask, uint8_t *agent_id, int64_t n) {
-    __shared__ __align__(16) uint32_t stage[WARPS][STAGE_WORDS];
+    __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
     if (first >= n) return;
     const bool valid = g < n;
     const int nvalid = (int)min((int64_t)32, n - first);
+    stage_init(stage[warp], lane);
     Env e;
     env_clear(e);
     if (valid) env_unpack(e, state[g]);
     uint32_t u, up, m0, m1;
     occupancy(e, u, up);
     legal_mask(e.xo, e.yo, u, up, m0, m1);
-    stage_bits(stage[warp], make_lane_cfg(lane), lane, e.s, m0, m1);
+    __syncwarp();
+    stage_env(stage[warp], make_lane_cfg(lane), lane, e, m0, m1);
     __syncwarp();
     emit_chunk<kStreaming>(stage[warp], lane, obs + first * GBL_OBS_BYTES, mask + first * GBL_MASK_BYTES, nvalid);
     if (agent_id && valid) agent_id[g] = (uint8_t)e.agent;
@@ -76,8 +78,8 @@ struct StepParams {
 };
 
 template <typename ActT, bool kStreaming>
-__global__ void __launch_bounds__(BLOCK) step_kernel(StepParams p) {
-    __shared__ __align__(16) uint32_t stage[WARPS][2][STAGE_WORDS];
+__global__ void __launch_bounds__(BLOCK, 4) step_kernel(StepParams p) {
+    __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
     const bool valid = g < p.n;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(StepParams p) {
     if (first < p.n) {
         const int nvalid = (int)min((int64_t)32, p.n - first);
         const LaneCfg cfg = make_lane_cfg(lane);
+        stage_init(stage[warp], lane);
         Env e;
         env_clear(e);
         uint32_t action = 255u;
@@ -103,9 +106,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(StepParams p) {
         if (same_step && !r.acted) r.term = false;     // skipped env: nothing to reset
         if (same_step) {
             if (p.final_obs && p.final_mask) {      // terminal observation before it is replaced
-                stage_bits(stage[warp][1], cfg, lane, e.s, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(stage[warp][1], lane, p.final_obs + first * GBL_OBS_BYTES,
+                stage_env(stage[warp], cfg, lane, e, m0, m1);
+                __syncwarp();
+                emit_chunk<kStreaming>(stage[warp], lane, p.final_obs + first * GBL_OBS_BYTES,
                                        p.final_mask + first * GBL_MASK_BYTES, nvalid);
             }
             if (r.term) {
@@ -114,9 +118,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(StepParams p) {
                 legal_mask(e.xo, e.yo, u, up, m0, m1);
             }
         }
-        stage_bits(stage[warp][0], cfg, lane, e.s, m0, m1);
         __syncwarp();
-        emit_chunk<kStreaming>(stage[warp][0], lane, p.obs + first * GBL_OBS_BYTES,
+        stage_env(stage[warp], cfg, lane, e, m0, m1);
+        __syncwarp();
+        emit_chunk<kStreaming>(stage[warp], lane, p.obs + first * GBL_OBS_BYTES,
                                p.mask + first * GBL_MASK_BYTES, nvalid);
         if (valid) {
             p.state[g] = env_pack(e);
@@ -146,8 +151,8 @@ struct RolloutParams {
 
 // kAux: any of rew_out / term_out / agent_out / action_log is requested (compiled out otherwise)
 template <bool kFast, bool kStreaming, bool kAux>
-__global__ void __launch_bounds__(BLOCK) rollout_kernel(RolloutParams p) {
-    __shared__ __align__(16) uint32_t stage[WARPS][2][STAGE_WORDS];
+__global__ void __launch_bounds__(BLOCK, 4) rollout_kernel(RolloutParams p) {
+    __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
     const bool valid = g < p.n;
@@ -159,13 +164,17 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(RolloutParams p) {
         Env e;
         env_clear(e);
         if (valid) env_unpack(e, p.state[g]);
+        const uint32_t plies_start = e.plies;
         uint32_t u, up, m0, m1;
         occupancy(e, u, up);
         legal_mask(e.xo, e.yo, u, up, m0, m1);
+        stage_init(stage[warp], lane);
+        __syncwarp();
         uint4 rnd = make_uint4(0, 0, 0, 0);
         uint32_t slot = (uint32_t)(p.step_base % (uint64_t)p.ring);
         const bool emit = p.obs_out != nullptr;
-        for (int32_t t = 0; t < p.T; ++t) {
+#pragma unroll 2
+        for (int32_t t = 0; t < p.T; ++t) {     // two plies per trip: the own/opponent register swap becomes renaming
             const uint64_t s = p.step_base + (uint64_t)t;
             if (t == 0 || (s & 3u) == 0) rnd = draw_block(p.seed, p.env_id_base + (uint64_t)g, s, 0u);
             uint32_t action = 255u;
@@ -182,15 +191,20 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(RolloutParams p) {
                 if (p.action_log) p.action_log[(int64_t)t * p.n + g] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
             if (emit) {
-                uint32_t *buf = stage[warp][t & 1];
-                stage_bits(buf, cfg, lane, e.s, m0, m1);
+                stage_env(stage[warp], cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(buf, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
+                emit_chunk<kStreaming>(stage[warp], lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
                                        p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid);
+                __syncwarp();
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
         }
         if (valid) p.state[g] = env_pack(e);
+        if (kFast) {   // every step was a live, legal step: these follow from the step count
+            st.steps = (uint32_t)p.T;
+            st.sumlen = plies_start + (uint32_t)p.T - e.plies;
+            st.p2w = st.episodes - st.p1w;
+        }
     }
     if (p.stats) flush_stats(st, valid, p.stats);
 }

@@ -10,15 +10,22 @@
 thread_local ShflCtx g_shfl;
 using namespace gbl;
 
+// one persistent staging area per emulated warp, like the __shared__ array of the kernels
+alignas(16) static uint8_t g_stage[STAGE_BYTES];
+static bool g_stage_ready = false;
+
 static void warp_emit(Env *e, uint32_t *m0, uint32_t *m1, int8_t *obs_chunk, int8_t *mask_chunk, int nvalid) {
-    uint32_t stage[STAGE_WORDS];
-    memset(stage, 0xAB, sizeof(stage));
+    if (!g_stage_ready) {
+        memset(g_stage, 0xAB, sizeof(g_stage));
+        for (int lane = 0; lane < 32; ++lane) stage_init(g_stage, lane);
+        g_stage_ready = true;
+    }
     for (int pass = 0; pass < 2; ++pass)
         for (int lane = 0; lane < 32; ++lane) {
             g_shfl.pass = pass; g_shfl.call = 0; g_shfl.lane = lane;
-            stage_bits(stage, make_lane_cfg(lane), lane, e[lane].s, m0[lane], m1[lane]);
+            stage_env(g_stage, make_lane_cfg(lane), lane, e[lane], m0[lane], m1[lane]);
         }
-    for (int lane = 0; lane < 32; ++lane) emit_chunk<true>(stage, lane, obs_chunk, mask_chunk, nvalid);
+    for (int lane = 0; lane < 32; ++lane) emit_chunk<true>(g_stage, lane, obs_chunk, mask_chunk, nvalid);
 }
 
 extern "C" __attribute__((visibility("default")))
@@ -29,10 +36,11 @@ void emul_rollout(unsigned long long *state, int64_t n, int32_t T, uint64_t seed
     const bool fast = same_step;
     for (int64_t first = 0; first < n; first += 32) {
         int nvalid = (int)std::min<int64_t>(32, n - first);
-        Env e[32]; uint32_t m0[32], m1[32]; uint4 rnd[32]; Stats st[32];
+        Env e[32]; uint32_t m0[32], m1[32], plies_start[32]; uint4 rnd[32]; Stats st[32];
         for (int l = 0; l < 32; ++l) {
             env_clear(e[l]); memset(&st[l], 0, sizeof(Stats));
             if (l < nvalid) env_unpack(e[l], {state[2 * (first + l)], state[2 * (first + l) + 1]});
+            plies_start[l] = e[l].plies;
             uint32_t u, up; occupancy(e[l], u, up); legal_mask(e[l].xo, e[l].yo, u, up, m0[l], m1[l]);
         }
         for (int32_t t = 0; t < T; ++t) {
@@ -57,6 +65,11 @@ void emul_rollout(unsigned long long *state, int64_t n, int32_t T, uint64_t seed
         for (int l = 0; l < nvalid; ++l) {
             ulonglong2 v = env_pack(e[l]);
             state[2 * (first + l)] = v.x; state[2 * (first + l) + 1] = v.y;
+            if (fast) {
+                st[l].steps = (uint32_t)T;
+                st[l].sumlen = plies_start[l] + (uint32_t)T - e[l].plies;
+                st[l].p2w = st[l].episodes - st[l].p1w;
+            }
             uint32_t a[8] = {st[l].episodes, st[l].p1w, st[l].p2w, st[l].steps, st[l].sumlen, st[l].illegal, st[l].both, st[l].maxlen};
             for (int i = 0; i < 7; ++i) stats[i] += a[i];
             stats[7] = std::max<int64_t>(stats[7], a[7]);
