@@ -38,34 +38,61 @@ def main():
     out = {"peak_hbm_gbs": peak}
     n = 1 << 20
 
-    # -- step_kernel, device resident: replay logged legal actions (uint8) -------------------------------
-    K = 48
+    # -- step_kernel, device resident: replay logged legal actions (uint8).  The 32 launches are captured in a
+    #    CUDA graph (state restored at its head) so the figure is the kernel's, not Python's launch rate. ----
+    K = 32
     logger = gobblet_v1.vec_env(n, device=dev, seed=2)
-    log = logger.rollout_random(K + 3, emit=False, log_actions=True)["actions"]
+    log = logger.rollout_random(K, emit=False, log_actions=True)["actions"]
     vec = gobblet_v1.vec_env(n, device=dev, seed=2)
-    # two alternating output slots > L2 so the stores go to DRAM
-    slots = [(torch.zeros((n, 3, 3, 13), dtype=torch.int8, device=dev), torch.zeros((n, 54), dtype=torch.int8, device=dev)) for _ in range(2)]
-    k = [0]
+    state0 = vec.state.clone()
+    # four alternating output slots (717 MB > L2) so the stores go to DRAM
+    slots = [(torch.zeros((n, 3, 3, 13), dtype=torch.int8, device=dev), torch.zeros((n, 54), dtype=torch.int8, device=dev)) for _ in range(4)]
 
-    def one_step():
-        vec.step(log[k[0]], out=slots[k[0] & 1])
-        k[0] += 1
+    def replay_steps():
+        vec.state.copy_(state0)
+        for k in range(K):
+            vec.step(log[k], out=slots[k & 3])
 
-    for _ in range(3):
-        one_step()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(K):
-        one_step()
-    b.record()
-    torch.cuda.synchronize()
-    dt = a.elapsed_time(b) * 1e-3 / K
+    replay_steps()
     assert torch.equal(vec.state, logger.state)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        replay_steps()
+        with torch.cuda.graph(g, stream=side):
+            replay_steps()
+    torch.cuda.current_stream().wait_stream(side)
+    dt_graph = timed(g.replay, 10) / K
+    assert torch.equal(vec.state, logger.state)
+    dt_eager = timed(replay_steps, 5) / K
     bytes_step = 171 + 32 + 1 + 5
-    out["step_kernel"] = {"envs": n, "env_steps_per_s": n / dt, "us_per_launch": dt * 1e6,
-                          "algorithmic_bytes_per_env_step": bytes_step, "achieved_gbs": n * bytes_step / dt / 1e9,
-                          "frac_of_peak": n * bytes_step / dt / 1e9 / peak}
+    out["step_kernel"] = {"envs": n, "env_steps_per_s": n / dt_graph, "us_per_launch_graph": dt_graph * 1e6,
+                          "us_per_launch_python_loop": dt_eager * 1e6,
+                          "algorithmic_bytes_per_env_step": bytes_step, "achieved_gbs": n * bytes_step / dt_graph / 1e9,
+                          "frac_of_peak": n * bytes_step / dt_graph / 1e9 / peak}
+
+    # -- BASELINE config 2 (4096 envs): per-step launches vs a CUDA graph of them vs one fused launch -----
+    n2, T2 = 4096, 256
+    small = gobblet_v1.vec_env(n2, device=dev, seed=0, graph_safe=True)
+
+    def per_step_launches():
+        for _ in range(T2):
+            small.rollout_random(1, ring=1)
+
+    dt_launch = timed(per_step_launches, 3) / T2
+    g2 = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        per_step_launches()
+        with torch.cuda.graph(g2, stream=side):
+            per_step_launches()
+    torch.cuda.current_stream().wait_stream(side)
+    dt_g2 = timed(g2.replay, 10) / T2
+    dt_fused = timed(lambda: small.rollout_random(T2, ring=4), 10) / T2
+    out["c2_4096_envs"] = {"per_step_launch_env_steps_per_s": n2 / dt_launch, "cuda_graph_env_steps_per_s": n2 / dt_g2,
+                           "fused_env_steps_per_s": n2 / dt_fused, "us_per_step": {"launch": dt_launch * 1e6, "graph": dt_g2 * 1e6, "fused": dt_fused * 1e6},
+                           "illegal_moves": int(small.stats[5])}
 
     # -- observe_kernel ------------------------------------------------------------------------------------
     dt = timed(lambda: vec.observe(), 50)

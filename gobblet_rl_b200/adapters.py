@@ -163,12 +163,16 @@ class VecCollector:
 class RandomLegalPolicy:
     """Uniform over the mask on the GPU (Philox): the vectorised form of example_basic.py:58-61."""
 
-    def __init__(self, seed: int = 0, env_id_base: int = 0):
+    def __init__(self, seed: int = 0, env_id_base: int = 0, graph_safe_device=None):
         self.seed, self.env_id_base, self.step = int(seed), int(env_id_base), 0
+        # graph_safe_device: keep the step counter in device memory (CUDA-graph capturable)
+        self.step_dev = None if graph_safe_device is None else torch.zeros(1, dtype=torch.int64, device=graph_safe_device)
 
     def __call__(self, obs, mask, agent_id=None):
         act = torch.empty(mask.shape[0], dtype=torch.int32, device=mask.device)
-        ops.sample_legal(mask.to(torch.int8).contiguous(), self.seed, self.env_id_base, self.step, act)
+        ops.sample_legal(mask.to(torch.int8).contiguous(), self.seed, self.env_id_base, self.step, act, self.step_dev)
+        if self.step_dev is not None:
+            self.step_dev += 1
         self.step += 1
         return act
 

@@ -140,6 +140,7 @@ struct RolloutParams {
     int64_t n;
     int32_t T;
     uint64_t seed, env_id_base, step_base;
+    const uint64_t *step_base_dev;
     int8_t *obs_out, *mask_out;
     int64_t obs_slot_stride, mask_slot_stride;
     int32_t ring;
@@ -170,12 +171,13 @@ __global__ void __launch_bounds__(BLOCK, 4) rollout_kernel(RolloutParams p) {
         legal_mask(e.xo, e.yo, u, up, m0, m1);
         stage_init(stage[warp], lane);
         __syncwarp();
+        const uint64_t step_base = p.step_base_dev ? *p.step_base_dev : p.step_base;
         uint4 rnd = make_uint4(0, 0, 0, 0);
-        uint32_t slot = (uint32_t)(p.step_base % (uint64_t)p.ring);
+        uint32_t slot = (uint32_t)(step_base % (uint64_t)p.ring);
         const bool emit = p.obs_out != nullptr;
 #pragma unroll 2
         for (int32_t t = 0; t < p.T; ++t) {     // two plies per trip: the own/opponent register swap becomes renaming
-            const uint64_t s = p.step_base + (uint64_t)t;
+            const uint64_t s = step_base + (uint64_t)t;
             if (t == 0 || (s & 3u) == 0) rnd = draw_block(p.seed, p.env_id_base + (uint64_t)g, s, 0u);
             uint32_t action = 255u;
             if (kFast || !e.done) action = sample_action(m0, m1, pick_word(rnd, (uint32_t)s & 3u));
@@ -212,9 +214,10 @@ __global__ void __launch_bounds__(BLOCK, 4) rollout_kernel(RolloutParams p) {
 // ---- masked-uniform sampler over int8 masks -----------------------------------------------------
 __global__ void __launch_bounds__(BLOCK)
 sample_legal_kernel(const int8_t *__restrict__ mask, uint64_t seed, uint64_t env_id_base, uint64_t step,
-                    int32_t *act, int64_t n) {
+                    const uint64_t *step_dev, int32_t *act, int64_t n) {
     int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (g >= n) return;
+    if (step_dev) step = *step_dev;
     const int8_t *m = mask + g * GBL_MASK_BYTES;
     uint32_t m0 = 0, m1 = 0;
     for (int a = 0; a < 32; ++a) m0 |= (uint32_t)(m[a] != 0) << a;
@@ -337,7 +340,7 @@ int gbl_step(void *state, const void *actions, int32_t action_bytes, int8_t *obs
 }
 
 int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_t env_id_base, uint64_t step_base,
-                       int8_t *obs_out, int8_t *mask_out, int64_t obs_slot_stride, int64_t mask_slot_stride,
+                       const uint64_t *step_base_dev, int8_t *obs_out, int8_t *mask_out, int64_t obs_slot_stride, int64_t mask_slot_stride,
                        int32_t ring, int8_t *rew_out, uint8_t *term_out, uint8_t *agent_out, uint8_t *action_log,
                        int64_t *stats, uint32_t flags, void *stream) {
     if (n < 0 || T < 0) return fail(GBL_E_INVALID, "gbl_rollout_random: n or T < 0");
@@ -353,7 +356,7 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     }
     if ((flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_MASK) return fail(GBL_E_INVALID, "gbl_rollout_random: bad autoreset mode");
     if (rew_out && (reinterpret_cast<uintptr_t>(rew_out) & 1u)) return fail(GBL_E_INVALID, "gbl_rollout_random: rew_out must be 2-byte aligned");
-    RolloutParams p = {(ulonglong2 *)state, n, T, seed, env_id_base, step_base, obs_out, mask_out,
+    RolloutParams p = {(ulonglong2 *)state, n, T, seed, env_id_base, step_base, step_base_dev, obs_out, mask_out,
                        obs_slot_stride, mask_slot_stride, ring, rew_out, term_out, agent_out, action_log, stats, flags};
     // random legal actions never hit the illegal path; with same-step auto-reset no env is ever dead
     const bool fast = (flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_SAME_STEP;
@@ -377,11 +380,12 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     return check_launch("gbl_rollout_random");
 }
 
-int gbl_sample_legal(const int8_t *mask, uint64_t seed, uint64_t env_id_base, uint64_t step, int32_t *act, int64_t n, void *stream) {
+int gbl_sample_legal(const int8_t *mask, uint64_t seed, uint64_t env_id_base, uint64_t step, const uint64_t *step_dev,
+                     int32_t *act, int64_t n, void *stream) {
     if (n < 0) return fail(GBL_E_INVALID, "gbl_sample_legal: n < 0");
     if (n == 0) return 0;
     if (!mask || !act) return fail(GBL_E_INVALID, "gbl_sample_legal: null pointer");
-    sample_legal_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(mask, seed, env_id_base, step, act, n);
+    sample_legal_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(mask, seed, env_id_base, step, step_dev, act, n);
     return check_launch("gbl_sample_legal");
 }
 

@@ -17,7 +17,7 @@ ILLEGAL_TERMINATE, ILLEGAL_PASS = 0x0, 0x1
 AUTORESET_OFF, AUTORESET_SAME_STEP, AUTORESET_NEXT_STEP = 0 << 1, 1 << 1, 2 << 1
 STORE_DEFAULT_POLICY = 0x8
 ACTION_SKIP_255 = 0x10
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _ILLEGAL = {"terminate": ILLEGAL_TERMINATE, "pass": ILLEGAL_PASS}
 _AUTORESET = {"off": AUTORESET_OFF, "same_step": AUTORESET_SAME_STEP, "next_step": AUTORESET_NEXT_STEP}
@@ -44,8 +44,8 @@ def _load():
         "gbl_reset_masked": (C.c_int, [vp, vp, i64, vp]),
         "gbl_observe": (C.c_int, [vp, vp, vp, vp, i64, vp]),
         "gbl_step": (C.c_int, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, u32, vp]),
-        "gbl_rollout_random": (C.c_int, [vp, i64, i32, u64, u64, u64, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, u32, vp]),
-        "gbl_sample_legal": (C.c_int, [vp, u64, u64, u64, vp, i64, vp]),
+        "gbl_rollout_random": (C.c_int, [vp, i64, i32, u64, u64, u64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, u32, vp]),
+        "gbl_sample_legal": (C.c_int, [vp, u64, u64, u64, vp, vp, i64, vp]),
         "gbl_greedy": (C.c_int, [vp, vp, vp, i32, u64, u64, vp, vp, vp, vp, i64, vp]),
         "gbl_export_squares": (C.c_int, [vp, vp, vp, i64, vp]),
         "gbl_import_squares": (C.c_int, [vp, vp, vp, i64, vp]),
@@ -133,9 +133,10 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
                    obs_out: Optional[torch.Tensor], mask_out: Optional[torch.Tensor],
                    rew_out: Optional[torch.Tensor], term_out: Optional[torch.Tensor],
                    agent_out: Optional[torch.Tensor], action_log: Optional[torch.Tensor],
-                   stats: Optional[torch.Tensor], flags: int) -> None:
-    """obs_out [ring, n, 3, 3, 13] / mask_out [ring, n, 54] (possibly views of padded slots)."""
-    dev = _need_cuda(state, rew_out, term_out, agent_out, action_log, stats)
+                   stats: Optional[torch.Tensor], flags: int, step_dev: Optional[torch.Tensor] = None) -> None:
+    """obs_out [ring, n, 3, 3, 13] / mask_out [ring, n, 54] (possibly views of padded slots).
+    step_dev: optional int64[1] CUDA tensor holding the absolute step (replaces step_base; graph-capturable)."""
+    dev = _need_cuda(state, rew_out, term_out, agent_out, action_log, stats, step_dev)
     n = state.shape[0]
     ring, so, sm = 1, 0, 0
     if obs_out is not None:
@@ -152,17 +153,18 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
         if t.shape[0] != ring:
             raise GobbletError("per-step outputs must share one ring length (that of obs_out when it is given)")
     with torch.cuda.device(dev):
-        _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(obs_out),
+        _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(step_dev), _ptr(obs_out),
                                       _ptr(mask_out), so, sm, ring, _ptr(rew_out), _ptr(term_out), _ptr(agent_out),
                                       _ptr(action_log), _ptr(stats), flags, _stream(state)))
 
 
 @torch.library.custom_op("gobblet_b200::sample_legal", mutates_args=("act",))
-def sample_legal(mask: torch.Tensor, seed: int, env_id_base: int, step: int, act: torch.Tensor) -> None:
-    dev = _need_cuda(mask, act)
+def sample_legal(mask: torch.Tensor, seed: int, env_id_base: int, step: int, act: torch.Tensor,
+                 step_dev: Optional[torch.Tensor] = None) -> None:
+    dev = _need_cuda(mask, act, step_dev)
     with torch.cuda.device(dev):
-        _check(LIB.gbl_sample_legal(_ptr(mask), seed & (2**64 - 1), env_id_base, step, _ptr(act), act.numel(),
-                                    _stream(mask)))
+        _check(LIB.gbl_sample_legal(_ptr(mask), seed & (2**64 - 1), env_id_base, step, _ptr(step_dev), _ptr(act),
+                                    act.numel(), _stream(mask)))
 
 
 @torch.library.custom_op("gobblet_b200::greedy", mutates_args=("act", "chosen", "cand", "used_fallback"))

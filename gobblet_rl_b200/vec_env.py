@@ -26,11 +26,12 @@ class VecEnv:
                   "off":       finished envs stay finished until `reset(ids)` (Tianshou's order)
     Outputs are views of persistent buffers, overwritten by the next call (pass `out=` to redirect).
     Global env ids `env_id_base + i` key the Philox sampler, so any sharding gives the same games.
+    graph_safe=True keeps the sampler's step counter on the device so rollouts can be CUDA-graph captured.
     """
 
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, illegal_mode: str = "terminate",
                  autoreset: str = "same_step", env_id_base: int = 0, streaming_stores: bool = True,
-                 skip255: bool = False):
+                 skip255: bool = False, graph_safe: bool = False):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -48,6 +49,9 @@ class VecEnv:
         self.agent_id = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.stats = torch.zeros(8, dtype=torch.int64, device=dev)
         self.step_count = 0          # absolute lockstep step index (Philox counter)
+        # graph_safe: the Philox step counter lives in device memory and is advanced by a torch op after
+        # every rollout, so `rollout_random` can be captured in a CUDA graph and replayed (small-N regime)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev) if graph_safe else None
         self.kernel_launches = 0
         self.reset()
 
@@ -113,7 +117,9 @@ class VecEnv:
             log = torch.zeros((T, n), dtype=torch.uint8, device=dev)
             out["actions"] = log
         ops.rollout_random(self.state, int(T), self.seed, self.env_id_base, self.step_count, obs_out, mask_out,
-                           rew_out, term_out, agent_out, log, self.stats, self.flags)
+                           rew_out, term_out, agent_out, log, self.stats, self.flags, self.step_dev)
+        if self.step_dev is not None:
+            self.step_dev += int(T)
         self.step_count += int(T)
         self.kernel_launches += 1
         return out

@@ -43,7 +43,7 @@ extern "C" {
 #define GBL_API
 #endif
 
-#define GBL_ABI_VERSION 1
+#define GBL_ABI_VERSION 2
 #define GBL_OBS_BYTES 117
 #define GBL_MASK_BYTES 54
 #define GBL_STATE_BYTES 16
@@ -92,18 +92,22 @@ GBL_API int gbl_step(void *state, const void *actions, int32_t action_bytes, int
  * popcount(mask)), the j-th legal action in ascending order (uniform over the mask, as
  * example_basic.py:58-61).  Per step the next observation and mask are written to ring slot
  * (step_base+t) % ring of obs_out / mask_out (slot strides in bytes, multiples of 16).
+ * step_base_dev (nullable, device uint64): when given it REPLACES step_base and is read by the kernel at
+ * launch, so a CUDA graph holding this launch advances through the Philox stream when the caller bumps
+ * the counter inside the same graph.
  * Nullable: obs_out+mask_out (simulate only), rew_out [ring][n][2], term_out [ring][n],
  * agent_out [ring][n], action_log [T][n] (255 = no action), stats. */
 GBL_API int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_t env_id_base,
-                       uint64_t step_base, int8_t *obs_out, int8_t *mask_out,
+                       uint64_t step_base, const uint64_t *step_base_dev, int8_t *obs_out, int8_t *mask_out,
                        int64_t obs_slot_stride, int64_t mask_slot_stride, int32_t ring,
                        int8_t *rew_out, uint8_t *term_out, uint8_t *agent_out, uint8_t *action_log,
                        int64_t *stats, uint32_t flags, void *stream);
 
 /* Uniform sample over each mask row with the same Philox stream as the rollout
- * (random_admissible_policy_rllib.py:23-30, example_basic.py:58-61).  act[i] = -1 for an empty row. */
+ * (random_admissible_policy_rllib.py:23-30, example_basic.py:58-61).  act[i] = -1 for an empty row.
+ * step_dev (nullable, device uint64) replaces `step` when given (see gbl_rollout_random). */
 GBL_API int gbl_sample_legal(const int8_t *mask, uint64_t seed, uint64_t env_id_base, uint64_t step,
-                     int32_t *act, int64_t n, void *stream);
+                     const uint64_t *step_dev, int32_t *act, int64_t n, void *stream);
 
 /* GreedyGobbletPolicy(depth).compute_action for n boards, one warp per board
  * (greedy_policy.py:38-221; depth 1 or 2).  prev3 (nullable): int16 [n][3], the agent's last three

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(ops.LIB_PATH)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.gbl_abi_version() == 1
+    assert lib.gbl_abi_version() == 2
     # the shipped SASS is sm_100a only, built from hand-written kernels (no PTX JIT, no other arch)
     out = subprocess.run(["cuobjdump", "-lelf", ops.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)

@@ -225,3 +225,35 @@ def test_million_env_properties(gv1):
     assert torch.equal(obs_ring[slot], obs) and torch.equal(mask_ring[slot], mask)
     # masks are 0/1 and every env has a legal move
     assert int(mask.max()) == 1 and int(mask.sum(1).min()) >= 1
+
+
+def test_cuda_graph_replay_of_rollouts_matches_oracle(gv1):
+    """graph_safe=True keeps the Philox step counter on the device: a captured launch replayed k times
+    walks the same random stream as k eager launches (BASELINE config 2, CUDA-graph variant)."""
+    n, T, reps = 300, 5, 4
+    v = gv1.vec_env(n, seed=13, graph_safe=True)
+    log = torch.zeros((reps + 1, T, n), dtype=torch.uint8, device="cuda")
+
+    def one(i):
+        out = v.rollout_random(T, ring=1, log_actions=True)
+        log[i].copy_(out["actions"])
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        one(0)                                           # eager warm-up launch: steps 0..T-1
+        idx = torch.zeros((), dtype=torch.int64, device="cuda")
+        with torch.cuda.graph(g, stream=side):
+            out = v.rollout_random(T, ring=1, log_actions=True)
+            captured = out["actions"]
+    torch.cuda.current_stream().wait_stream(side)
+    for i in range(1, reps + 1):
+        g.replay()
+        log[i].copy_(captured)
+    torch.cuda.synchronize()
+    o = O.VecOracle(n)
+    want = o.rollout_random(T * (reps + 1), seed=13)
+    assert np.array_equal(log.cpu().numpy().reshape(-1, n), want["actions"])
+    assert v.stats.tolist()[:7] == o.stats.tolist()[:7]
+    assert int(v.step_dev) == T * (reps + 1)
