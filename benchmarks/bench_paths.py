@@ -153,6 +153,25 @@ def main():
                                     "illegal_moves": int(v5.stats[5]), "note": "includes fp16 MLP inference + masked eps-greedy in torch"}
     dt = timed(lambda: adapters.VecCollector(v5, adapters.RandomLegalPolicy(seed=3), buf).collect(), 10)
     out["collect_random_policy"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt}
+    # -- the drop-in facade: gobblet_v1.env() driven by the reference's own loop (example_basic.py:50-67) ------
+    import time
+
+    import numpy as np
+    env = gobblet_v1.env(render_mode=None)
+    np.random.seed(0)
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 3.0:
+        env.reset()
+        for agent in env.agent_iter():
+            obs, reward, term, trunc, info = env.last()
+            if term or trunc:
+                env.step(None)
+            else:
+                m = obs["action_mask"]
+                env.step(np.random.choice(np.arange(len(m)), p=m / np.sum(m)))
+                steps += 1
+    out["facade_env_loop"] = {"env_steps_per_s": steps / (time.perf_counter() - t0),
+                              "note": "batch-of-1 AEC facade: one kernel launch + one device->host read per step"}
     print(json.dumps(out, indent=1))
 
 

@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["gobblet_engine.cu", "gobblet_greedy.cu"]
 HEADERS = ["gobblet_core.cuh", os.path.join("..", "..", "include", "gobblet_b200.h")]
-OUT = os.path.join(HERE, "libgobblet_b200.so")
+# tuning builds: GBL_EXTRA_NVCC_FLAGS="-DGBL_BLOCK=128" GBL_LIB_SUFFIX=_b128 python build.py
+OUT = os.path.join(HERE, "libgobblet_b200" + os.environ.get("GBL_LIB_SUFFIX", "") + ".so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
 
@@ -23,7 +24,8 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     tmp = OUT + f".tmp{os.getpid()}"
-    cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", tmp, *[os.path.join(HERE, s) for s in SOURCES]]
+    extra = os.environ.get("GBL_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-shared", "-o", tmp, *[os.path.join(HERE, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

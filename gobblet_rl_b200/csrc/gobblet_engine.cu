@@ -10,7 +10,10 @@
 
 namespace gbl {
 
-constexpr int BLOCK = 256, WARPS = BLOCK / 32;
+#ifndef GBL_BLOCK
+#define GBL_BLOCK 256   // threads per block (tuning knob; 256 measured best on B200)
+#endif
+constexpr int BLOCK = GBL_BLOCK, WARPS = BLOCK / 32, MIN_BLOCKS = 1024 / BLOCK;
 
 // ---- block-level statistics reduction: shuffles -> shared -> one atomic per slot per block ----
 __device__ __forceinline__ void flush_stats(const Stats &st, bool valid, int64_t *stats) {
@@ -78,7 +81,7 @@ struct StepParams {
 };
 
 template <typename ActT, bool kStreaming>
-__global__ void __launch_bounds__(BLOCK, 4) step_kernel(StepParams p) {
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) step_kernel(StepParams p) {
     __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
@@ -152,7 +155,7 @@ struct RolloutParams {
 
 // kAux: any of rew_out / term_out / agent_out / action_log is requested (compiled out otherwise)
 template <bool kFast, bool kStreaming, bool kAux>
-__global__ void __launch_bounds__(BLOCK, 4) rollout_kernel(RolloutParams p) {
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) rollout_kernel(RolloutParams p) {
     __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;

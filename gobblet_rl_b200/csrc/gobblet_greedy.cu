@@ -22,11 +22,29 @@ __device__ __forceinline__ void apply_xy(uint32_t &x, uint32_t &y, uint32_t acti
     if (k & 1u) y = (y & ~field) | bit; else x = (x & ~field) | bit;
 }
 
-// check_for_winner after a move, relative to (mine, theirs): +1 / -1 / 0   (board.py:183-194)
-__device__ __forceinline__ int winner_of(uint32_t xm, uint32_t ym, uint32_t xt, uint32_t yt) {
+// Complete-line sets for every 9-bit "squares I own on top" mask: bit i = line i of board.py:135-153 is
+// complete.  The search evaluates ~3000 positions per board and the integer pipe is its bottleneck (ncu:
+// ALU 80 % busy, LSU idle), so the 8-line test (26 ALU instructions) is a 512-byte shared-memory lookup here.
+struct LineLut { uint8_t v[512]; };
+constexpr LineLut make_line_lut() {
+    LineLut t{};
+    const int L[8][3] = {{0, 1, 2}, {3, 4, 5}, {6, 7, 8}, {0, 3, 6}, {1, 4, 7}, {2, 5, 8}, {0, 4, 8}, {2, 4, 6}};
+    for (int m = 0; m < 512; ++m) {
+        int b = 0;
+        for (int l = 0; l < 8; ++l)
+            if (((m >> L[l][0]) & (m >> L[l][1]) & (m >> L[l][2])) & 1) b |= 1 << l;
+        t.v[m] = (uint8_t)b;
+    }
+    return t;
+}
+__device__ const LineLut kLineLut = make_line_lut();
+
+// check_for_winner after a move, relative to (mine, theirs): +1 / -1 / 0   (board.py:183-194): the owner
+// of the highest-index complete line wins, i.e. the larger of the two line sets (they share no line)
+__device__ __forceinline__ int winner_of(const uint8_t *lut, uint32_t xm, uint32_t ym, uint32_t xt, uint32_t yt) {
     uint32_t occ = xm | ym | xt | yt, u = occ | (occ >> 9) | (occ >> 18), up = u >> 9;
-    bool both;
-    return winner_rel(tops(xm, ym, up), tops(xt, yt, up), both);
+    uint32_t lm = lut[tops(xm, ym, up)], lt = lut[tops(xt, yt, up)];
+    return (lm > lt) - (lt > lm);
 }
 
 __device__ __forceinline__ uint64_t ballot64(bool lo, bool hi) {
@@ -37,6 +55,9 @@ __global__ void __launch_bounds__(GREEDY_BLOCK)
 greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, const int16_t *__restrict__ prev3,
               int32_t depth, uint64_t seed, uint64_t ctr_base, int32_t *act, int32_t *chosen_out,
               uint64_t *cand_out, uint8_t *fallback_out, int64_t n) {
+    __shared__ __align__(16) uint8_t lut[512];
+    reinterpret_cast<uint16_t *>(lut)[threadIdx.x] = reinterpret_cast<const uint16_t *>(kLineLut.v)[threadIdx.x];
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * GREEDY_WARPS + (threadIdx.x >> 5);
     if (b >= n) return;
@@ -85,7 +106,7 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
         if (a < 54u && ((legal0 & maskbits) >> a) & 1ull) {
             uint32_t x = xo, y = yo;
             apply_xy(x, y, a);
-            w = winner_of(x, y, xp, yp);
+            w = winner_of(lut, x, y, xp, yp);
         }
         win[r] = w > 0; loss[r] = w < 0;
     }
@@ -120,7 +141,7 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
                 if ((replies >> a2) & 1ull) {
                     uint32_t x2 = xp, y2 = yp;
                     apply_xy(x2, y2, a2);
-                    w = winner_of(x1, y1, x2, y2);
+                    w = winner_of(lut, x1, y1, x2, y2);
                 } else a2 = 64u;
                 theirs[r] = a2 < 64u && w < 0;
                 notmine[r] = a2 < 64u && w <= 0;

@@ -69,6 +69,8 @@ class raw_env(AECEnv):
         # one env of the batched engine; illegal moves pass the turn like the reference's raw_env
         self._vec = VecEnv(1, device=device, illegal_mode="pass", autoreset="off")
         self._scratch = None
+        self._bind_outputs()
+        self._vec.observe()
         self.board = _BoardView(self)
         self.board_size = 3
         self.agents = ["player_1", "player_2"]
@@ -93,17 +95,27 @@ class raw_env(AECEnv):
         self.screen = None
         self._pull()
 
-    # one device->host read per step: obs(117) | mask(54) | rew(2) | terminated | agent_id
+    # All per-step outputs of the engine land in ONE 256-byte device buffer, so a step costs one kernel launch
+    # and one device->host read: obs @0 (117 B) | mask @128 (54 B) | rew @192 | terminated @194 | truncated
+    # @195 | agent_id @196.
+    def _bind_outputs(self):
+        v, b = self._vec, torch.zeros(256, dtype=torch.uint8, device=self._vec.device)
+        self._buf = b
+        v.obs = b[0:117].view(torch.int8).view(1, 3, 3, 13)
+        v.mask = b[128:182].view(torch.int8).view(1, 54)
+        v.rew = b[192:194].view(torch.int8).view(1, 2)
+        v.terminated = b[194:195].view(torch.bool)
+        v.truncated = b[195:196].view(torch.bool)
+        v.agent_id = b[196:197]
+        self._act = torch.zeros(1, dtype=torch.int64, device=v.device)
+
     def _pull(self):
-        v = self._vec
-        packed = torch.cat([v.obs.reshape(-1).view(torch.uint8), v.mask.reshape(-1).view(torch.uint8),
-                            v.rew.reshape(-1).view(torch.uint8), v.terminated.view(torch.uint8),
-                            v.agent_id]).cpu().numpy()
-        self._obs = packed[:117].view(np.int8).reshape(3, 3, 13).copy()
-        self._mask = packed[117:171].view(np.int8).copy()
-        self._rew = packed[171:173].view(np.int8).astype(int)
-        self._term = bool(packed[173])
-        self._sel = int(packed[174])
+        host = self._buf.cpu().numpy()
+        self._obs = host[:117].view(np.int8).reshape(3, 3, 13)
+        self._mask = host[128:182].view(np.int8)
+        self._rew = host[192:194].view(np.int8).astype(int)
+        self._term = bool(host[194])
+        self._sel = int(host[196])
 
     def observe(self, agent):                                   # gobblet.py:179-215
         # the reference indexes the LIVE agent list (gobblet.py:182, :199, :225): once a dead step has
@@ -140,7 +152,7 @@ class raw_env(AECEnv):
     def step(self, action):                                     # gobblet.py:231-273
         if self.terminations[self.agent_selection] or self.truncations[self.agent_selection]:
             return self._was_dead_step(action)
-        self._vec.step(torch.tensor([int(action)], dtype=torch.int64, device=self._vec.device))
+        self._vec.step(self._act.fill_(int(action)))
         self._pull()
         next_agent = self._agent_selector.next()
         if self._term:

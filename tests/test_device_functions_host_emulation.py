@@ -96,3 +96,31 @@ def test_step_with_arbitrary_actions_matches_oracle(emul, illegal_mode, autorese
         mask = w[1]
     assert stats.tolist() == v.stats.tolist()
     assert stats[5] > 0
+
+
+def test_hypothesis_action_sequences(emul):
+    """Property test (the reference lists hypothesis as a dev dependency but never uses it): ANY sequence of
+    integers fed as actions -- legal, illegal, out of range -- leaves engine and oracle in lockstep."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.lists(st.integers(min_value=-2, max_value=58), min_size=1, max_size=60),
+           st.sampled_from(["terminate", "pass"]), st.sampled_from(["same_step", "off", "next_step"]))
+    def run(actions, illegal_mode, autoreset):
+        fl = O.flags(illegal_mode, autoreset)
+        v = O.VecOracle(1, illegal_mode, autoreset)
+        state = np.zeros((1, 2), np.uint64)
+        stats = np.zeros(8, np.int64)
+        for a in actions:
+            acts = np.array([a], np.int64)
+            obs = np.zeros((1, 3, 3, 13), np.int8); msk = np.zeros((1, 54), np.int8)
+            rew = np.zeros((1, 2), np.int8); term = np.zeros(1, np.uint8); trunc = np.zeros(1, np.uint8)
+            agent = np.zeros(1, np.uint8)
+            emul.emul_step(_p(state), C.c_int64(1), _p(acts), C.c_uint32(fl), _p(obs), _p(msk), _p(rew), _p(term),
+                           _p(trunc), _p(agent), None, None, _p(stats))
+            w = v.step(acts)
+            assert np.array_equal(obs, w[0]) and np.array_equal(msk, w[1]) and np.array_equal(rew, w[2])
+            assert bool(term[0]) == bool(w[3][0]) and bool(trunc[0]) == bool(w[4][0]) and agent[0] == w[5][0]
+        assert stats.tolist() == v.stats.tolist()
+
+    run()

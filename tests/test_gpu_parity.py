@@ -257,3 +257,17 @@ def test_cuda_graph_replay_of_rollouts_matches_oracle(gv1):
     assert np.array_equal(log.cpu().numpy().reshape(-1, n), want["actions"])
     assert v.stats.tolist()[:7] == o.stats.tolist()[:7]
     assert int(v.step_dev) == T * (reps + 1)
+
+
+def test_checkpoint_resume(gv1):
+    """The state tensor + counters are the whole env state: save, keep running, restore,
+    rerun -> identical trajectories."""
+    v = gv1.vec_env(500, seed=31)
+    v.rollout_random(17, emit=False)
+    ckpt = v.state_dict()
+    a = v.rollout_random(23, ring=1, log_actions=True)["actions"].clone()
+    end_state, end_stats = v.state.clone(), v.stats.clone()
+    w = gv1.vec_env(500, seed=0)
+    w.load_state_dict(ckpt)
+    b = w.rollout_random(23, ring=1, log_actions=True)["actions"]
+    assert torch.equal(a, b) and torch.equal(w.state, end_state) and torch.equal(w.stats, end_stats)
