@@ -2,6 +2,11 @@
 """GPU-resident rollout collection in the shape Tianshou's DQN example consumes
 (gobblet_rl/examples/example_tianshou_DQN.py:161-166, :401-409): an MLP 117 -> 128x4 -> 54 picks masked
 epsilon-greedy actions, the step kernel writes obs / mask / reward / flags straight into a TrajectoryBuffer."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
 import torch
 
 from gobblet_rl_b200 import adapters, gobblet_v1

@@ -1,6 +1,11 @@
 #!/usr/bin/env python
 """Greedy vs greedy, the loop of tutorials/GreedyAgent/tutorial_greedy.py:24-50 (first two plies random),
 then the batched search: one warp per board for 65 536 boards."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
 import numpy as np
 import torch
 

@@ -1,6 +1,11 @@
 #!/usr/bin/env python
 """The reference's random-legal rollout (gobblet_rl/examples/example_basic.py:44-67, render_mode=None),
 unchanged except for the import -- then the same workload on the vectorised entry point."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
 import argparse
 
 import numpy as np
