@@ -57,7 +57,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index, period_ms=50):
+    def __init__(self, gpu_index, period_ms=20):
         self.gpu, self.rows, self.proc = gpu_index, [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -72,12 +72,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
+        """windows: [(t0, t1), ...] wall-clock intervals during which the GPU was under the benchmark's load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "power_w_max": None, "reasons": [], "samples": 0}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 8]
+        rows = [r for t, r in ok if any(a <= t <= b + 0.03 for a, b in windows)] or [r for _, r in ok]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "power_w_max": None, "reasons": [], "samples": 0}
         sm = sorted(float(r[1]) for r in rows)
@@ -238,7 +240,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks
     elapsed_ms = t.item()
     gpu_launches = vec.kernel_launches - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    load_windows = [(t_wall0, t_wall1)]
     stats = sharding.all_reduce_stats(vec.stats)      # the run's only collective (NCCL), untimed
 
     total_env_steps = world * n * T * a.steps
@@ -257,11 +259,12 @@ def main():
         for k in range(we):
             host.step(h_log[k])
         sync_all()
-        t0 = time.perf_counter()
+        t0, w0 = time.perf_counter(), time.time()
         for k in range(we, we + ke):
             host.step(h_log[k])                       # synchronises: results are in host memory
         torch.cuda.synchronize(dev)
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        load_windows.append((w0, time.time()))
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         final = torch.cat([e.state for e in host.envs])
@@ -270,6 +273,8 @@ def main():
                "d2h_bytes_per_step": host.d2h_bytes_per_step, "lockstep_steps": ke,
                "api": "HostVecEnv.step(pinned uint8 actions) -> pinned obs/mask/rew/terminated/truncated/agent_id"}
 
+    # clocks are sampled over the timed launches (and the e2e steps, which keep the GPU busy too)
+    clocks = sampler.stop(load_windows) if sampler else None
     if rank != 0:
         if world > 1:
             dist.barrier()

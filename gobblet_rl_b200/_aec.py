@@ -7,9 +7,9 @@ reward accumulation, dead steps, and the illegal-move / bounds / ordering wrappe
 """
 
 try:  # pragma: no cover - pettingzoo is not in the build image
-    from pettingzoo import AECEnv
-    from pettingzoo.utils import agent_selector
-    from pettingzoo.utils.wrappers import (AssertOutOfBoundsWrapper, BaseWrapper, OrderEnforcingWrapper,
+    from pettingzoo import AECEnv  # noqa: F401
+    from pettingzoo.utils import agent_selector  # noqa: F401
+    from pettingzoo.utils.wrappers import (AssertOutOfBoundsWrapper, BaseWrapper, OrderEnforcingWrapper,  # noqa: F401
                                            TerminateIllegalWrapper)
 
     HAVE_PETTINGZOO = True

@@ -5,7 +5,6 @@ sm_100a kernels behind the C ABI.  There is NO fallback: if the library cannot b
 with nvcc) importing this module raises.
 """
 import ctypes as C
-import os
 from typing import Optional
 
 import torch
