@@ -1,4 +1,5 @@
 """Build libgobblet_b200.so for sm_100a, in-tree (the .so is git-ignored but travels with gpurun)."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -12,11 +13,21 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
 
 
+def _fingerprint():
+    """Content hash of sources + flags: mtimes do not survive a snapshot copy to another box."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + os.environ.get("GBL_EXTRA_NVCC_FLAGS", "").split()).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def stale():
-    if not os.path.exists(OUT):
+    stamp = OUT + ".srchash"
+    if not (os.path.exists(OUT) and os.path.exists(stamp)):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS + ["build.py"])
+    with open(stamp) as fh:
+        return fh.read().strip() != _fingerprint()
 
 
 def build(force=False, verbose=False):
@@ -31,6 +42,9 @@ def build(force=False, verbose=False):
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     os.replace(tmp, OUT)
+    with open(OUT + ".srchash.tmp%d" % os.getpid(), "w") as fh:
+        fh.write(_fingerprint())
+    os.replace(fh.name, OUT + ".srchash")
     return OUT
 
 
