@@ -177,6 +177,30 @@ class RandomLegalPolicy:
         return act
 
 
+class GreedyVecPolicy:
+    """Depth-1/2 greedy policy for a whole VecEnv: one warp per board, with the repetition history of
+    greedy_policy.py:211-219 kept ON THE GPU as int16 [N, 2, 3] (last three actions per env and per agent).
+    The reference shares one history list per agent across everything a policy object is asked (SURVEY Q12d);
+    a vectorised env has N independent games, so the history is per env here, and `reset_history(done)`
+    clears it for finished games."""
+
+    def __init__(self, num_envs: int, depth: int = 2, seed: int = 0, device="cuda"):
+        self.depth, self.seed, self.calls = int(depth), int(seed), 0
+        self.prev = torch.full((int(num_envs), 2, 3), -1, dtype=torch.int16, device=device)
+        self._rows = torch.arange(int(num_envs), device=device)
+
+    def __call__(self, obs, mask, agent_id):
+        who = agent_id.long()
+        prev3 = self.prev[self._rows, who]                               # [N,3] history of the agent to move
+        act = greedy_actions(obs, mask, prev3, depth=self.depth, seed=self.seed, ctr_base=self.calls * obs.shape[0])
+        self.prev[self._rows, who] = torch.cat([prev3[:, 1:], act.to(torch.int16)[:, None]], dim=1)
+        self.calls += 1
+        return act
+
+    def reset_history(self, done):
+        self.prev[done] = -1
+
+
 class RandomAdmissiblePolicy:
     """random_admissible_policy_rllib.py:15-40: `compute_actions(obs_batch) -> (actions, [], {})`."""
 

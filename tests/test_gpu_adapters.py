@@ -129,3 +129,36 @@ def test_random_admissible_policy(ad):
     acts, state, info = ad.RandomAdmissiblePolicy(seed=4).compute_actions({"action_mask": masks})
     assert state == [] and info == {} and all(masks[i, a] == 1 for i, a in enumerate(acts))
     assert len(set(acts)) > 20
+
+
+def test_greedy_vec_policy_self_play_matches_oracle(ad):
+    """Greedy-vs-greedy self play of 400 envs on the GPU (tutorial_greedy.py:30-44 shape, two random plies
+    first): every move must be the one the oracle restatement of greedy_policy.py allows given the per-env
+    history, and the env transitions must match the oracle env."""
+    from gobblet_rl_b200 import gobblet_v1
+    n, T = 400, 14
+    vec = gobblet_v1.vec_env(n, seed=8, autoreset="off")
+    vec.rollout_random(2, emit=False)
+    o = O.VecOracle(n, "terminate", "off")
+    o.rollout_random(2, seed=8, per_step=False)
+    pol = ad.GreedyVecPolicy(n, depth=2, seed=4)
+    hist = [[[], []] for _ in range(n)]
+    obs, mask, agent = vec.observe()
+    n_fb = 0
+    for t in range(T):
+        act = pol(obs, mask, agent)
+        a_np, ag_np, obs_np, mask_np = act.cpu().numpy(), agent.cpu().numpy(), obs.cpu().numpy(), mask.cpu().numpy()
+        done = vec.terminated.cpu().numpy() if t else np.zeros(n, bool)
+        for i in range(0, n, 3):
+            if done[i]:
+                continue
+            h = hist[i][ag_np[i]]
+            chosen, cand, fb = O.greedy(obs_np[i], mask_np[i], (h[-3:] + [-1, -1, -1])[:3] if len(h) < 3 else h[-3:], 2)
+            assert (a_np[i] in cand) if fb else (a_np[i] == chosen), (t, i)
+            n_fb += fb
+        for i in range(n):
+            hist[i][ag_np[i]].append(int(a_np[i]))
+        obs, mask, rew, term, trunc, agent = vec.step(act)
+        w = o.step(a_np.astype(np.int64))
+        assert np.array_equal(obs.cpu().numpy(), w[0]) and np.array_equal(term.cpu().numpy(), w[3])
+    assert vec.stats[5] == 0 and vec.stats[0] > 0 and n_fb > 0
