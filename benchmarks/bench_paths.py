@@ -172,6 +172,32 @@ def main():
                 steps += 1
     out["facade_env_loop"] = {"env_steps_per_s": steps / (time.perf_counter() - t0),
                               "note": "batch-of-1 AEC facade: one kernel launch + one device->host read per step"}
+    # -- the reference's CPU numbers for the same rows (1 core), when its tree travelled in baseline/_ref ------
+    try:
+        from oracle import reference_loader as RL
+        if RL.available():
+            Board = RL.load_board().Board
+            gp = RL.load_greedy()
+            rng = np.random.default_rng(0)
+            t0, steps = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 5.0:          # Board-only rollout: 54 x is_legal + play_turn + winner
+                b, agent = Board(), 0
+                while True:
+                    legal = [a for a in range(54) if b.is_legal(a, agent)]
+                    b.play_turn(agent, int(rng.choice(legal)))
+                    steps += 1
+                    agent = 1 - agent
+                    if b.check_game_over():
+                        break
+            out["cpu_reference_board_only"] = {"env_steps_per_s": steps / (time.perf_counter() - t0), "cores": 1}
+            pol = gp.GreedyGobbletPolicy(depth=2)
+            o_np, m_np = gobs[:24].cpu().numpy(), gmask[:24].cpu().numpy()
+            t0 = time.perf_counter()
+            for i in range(24):
+                pol.compute_action(o_np[i], m_np[i])
+            out["cpu_reference_greedy_depth2"] = {"boards_per_s": 24 / (time.perf_counter() - t0), "cores": 1}
+    except Exception as exc:  # measurement aid only
+        out["cpu_reference_error"] = repr(exc)
     print(json.dumps(out, indent=1))
 
 

@@ -271,3 +271,36 @@ def test_checkpoint_resume(gv1):
     w.load_state_dict(ckpt)
     b = w.rollout_random(23, ring=1, log_actions=True)["actions"]
     assert torch.equal(a, b) and torch.equal(w.state, end_state) and torch.equal(w.stats, end_stats)
+
+
+def test_empty_and_degenerate_sizes(gv1):
+    """n = 0 and T = 0 are no-ops at the C ABI; ring shorter than T keeps the last `ring` steps."""
+    from gobblet_rl_b200 import ops
+    lib = ops.LIB
+    assert lib.gbl_reset(None, 0, None) == 0 and lib.gbl_observe(None, None, None, None, 0, None) == 0
+    assert lib.gbl_step(None, None, 8, None, None, None, None, None, None, None, None, None, 0, 0, None) == 0
+    assert lib.gbl_greedy(None, None, None, 2, 0, 0, None, None, None, None, 0, None) == 0
+    v = gv1.vec_env(77, seed=2)
+    before = v.state.clone()
+    ops.rollout_random(v.state, 0, 2, 0, 0, None, None, None, None, None, None, v.stats, v.flags)
+    assert torch.equal(v.state, before)
+    out = v.rollout_random(10, ring=3)
+    o = O.VecOracle(77)
+    want = o.rollout_random(10, seed=2)
+    for s in (7, 8, 9):                                   # ring slot of absolute step s is s % 3
+        assert np.array_equal(_np(out["obs"][s % 3]), want["obs"][s])
+        assert np.array_equal(_np(out["mask"][s % 3]), want["mask"][s])
+
+
+def test_empty_mask_and_full_board_greedy_inputs(gv1):
+    """gbl_greedy on degenerate inputs: an empty mask yields act = -1 with the fallback flag set (the reference
+    raises inside np.random.choice); a mask inconsistent with the board only ever returns masked actions."""
+    obs = torch.zeros((3, 3, 3, 13), dtype=torch.int8, device="cuda")
+    mask = torch.zeros((3, 54), dtype=torch.int8, device="cuda")
+    mask[1, 5] = 1
+    mask[2] = 1
+    act, chosen, cand, fb = gv1.greedy_actions(obs, mask, None, depth=2, details=True)
+    assert act[0].item() == -1 and fb[0].item() and cand[0].item() == 0
+    assert act[1].item() == 5 and act[2].item() in range(54)
+    wc, wcand, wfb = O.greedy(_np(obs)[2], _np(mask)[2], (-1, -1, -1), 2)
+    assert (chosen[2].item(), bool(fb[2])) == (wc, wfb)
