@@ -318,6 +318,40 @@ __device__ __forceinline__ void scatter_pieces(uint8_t *mine, uint32_t w, int pl
     }
 }
 
+// TMA bulk store (cp.async.bulk, SASS UBLKCP.G.S) of the observation image: one lane hands the 3744-byte
+// image to the copy engine instead of 32 lanes looping LDS.128 -> STG.128.  Compile-time choice (build.py).
+#ifndef GBL_BULK_STORE
+#define GBL_BULK_STORE 1
+#endif
+#if defined(__CUDA_ARCH__) && GBL_BULK_STORE
+constexpr bool kBulkStore = true;
+#else
+constexpr bool kBulkStore = false;
+#endif
+
+__device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, uint32_t bytes) {
+#ifdef __CUDA_ARCH__
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_store_wait_read() {   // the shared-memory source may be overwritten
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_store_wait_all() {    // the global writes have been performed
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void fence_smem_for_bulk() {    // generic-proxy smem writes -> visible to the copy engine
+#ifdef __CUDA_ARCH__
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
 // stage: all 32 lanes of the warp must call (shuffle inside).  stage = this warp's STAGE_BYTES.
 // The caller puts a __syncwarp() between stage_env and emit_chunk and one after emit_chunk.
 __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint32_t lane, const Env &e,
@@ -338,6 +372,7 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
     if (lane == 0) prev = 0;
     mbits[c.mfo] = v0 | prev;
     if (c.mn2) mbits[c.mfo + 1] = v1;
+    if (kBulkStore) fence_smem_for_bulk();
 }
 
 // copy / expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this
@@ -349,19 +384,32 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
     const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage + OBS_IMG_BYTES);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid == 32) {
+        if (kBulkStore) {
+            if (lane == 0) bulk_store_issue(obs_chunk, stage, OBS_IMG_BYTES);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t q = lane + 32u * i;
-            if (i < 7 || q < OBS_VEC) {
-                uint4 v = img[q];
-                img[q] = zero;
-                store16<kStreaming>(obs_chunk + 16u * q, v);
+            for (int i = 0; i < 8; ++i) {
+                uint32_t q = lane + 32u * i;
+                if (i < 7 || q < OBS_VEC) {
+                    uint4 v = img[q];
+                    img[q] = zero;
+                    store16<kStreaming>(obs_chunk + 16u * q, v);
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint32_t q = lane + 32u * i;
             if (i < 3 || q < MASK_VEC) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
+        }
+        if (kBulkStore) {                      // re-zero the image once the copy engine has read it
+            if (lane == 0) bulk_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t q = lane + 32u * i;
+                if (i < 7 || q < OBS_VEC) img[q] = zero;
+            }
         }
     } else {  // ragged last warp: vector stores while fully inside, bytes at the edge
         const uint32_t ob = 117u * nvalid, mb = 54u * nvalid;

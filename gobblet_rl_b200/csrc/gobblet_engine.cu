@@ -66,6 +66,7 @@ observe_kernel(const ulonglong2 *__restrict__ state, int8_t *obs, int8_t *mask, 
     __syncwarp();
     emit_chunk<kStreaming>(stage[warp], lane, obs + first * GBL_OBS_BYTES, mask + first * GBL_MASK_BYTES, nvalid);
     if (agent_id && valid) agent_id[g] = (uint8_t)e.agent;
+    if (kBulkStore && lane == 0) bulk_store_wait_all();
 }
 
 // ---- externally driven step ----------------------------------------------------------------------
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) step_kernel(StepParams p) {
         __syncwarp();
         emit_chunk<kStreaming>(stage[warp], lane, p.obs + first * GBL_OBS_BYTES,
                                p.mask + first * GBL_MASK_BYTES, nvalid);
+        if (kBulkStore && lane == 0) bulk_store_wait_all();
         if (valid) {
             p.state[g] = env_pack(e);
             if (p.rew2) *reinterpret_cast<char2 *>(p.rew2 + 2 * g) = make_char2((signed char)r.r1, (signed char)r.r2);
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) rollout_kernel(RolloutParam
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
         }
+        if (kBulkStore && lane == 0) bulk_store_wait_all();
         if (valid) p.state[g] = env_pack(e);
         if (kFast) {   // every step was a live, legal step: these follow from the step count
             st.steps = (uint32_t)p.T;

@@ -36,3 +36,4 @@ static inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, int delta) {
     return g_shfl.lane >= delta ? g_shfl.rec[c][g_shfl.lane - delta] : v;
 }
 static inline void __stcs(uint4 *p, uint4 v) { *p = v; }
+static inline void __syncwarp() {}   // lanes are emulated one after the other
