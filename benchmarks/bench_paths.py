@@ -129,7 +129,7 @@ def main():
     net = torch.nn.Sequential(torch.nn.Linear(117, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
                               torch.nn.Linear(128, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
                               torch.nn.Linear(128, 54)).to(dev).half()
-    eps_sampler = adapters.RandomLegalPolicy(seed=3)
+    eps_sampler = adapters.RandomLegalPolicy(seed=3, graph_safe_device=dev)
 
     @torch.no_grad()
     def policy(obs, mask, agent):
@@ -149,7 +149,10 @@ def main():
         col.roll()
 
     dt = timed(collect, 10)
-    out["collect_mlp_policy_c5"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt, "buffer_bytes": buf.nbytes(),
+    graph5 = col.capture()
+    dt_graph = timed(graph5.replay, 10)
+    out["collect_mlp_policy_c5"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt,
+                                    "env_steps_per_s_cuda_graph": n5 * T5 / dt_graph, "buffer_bytes": buf.nbytes(),
                                     "illegal_moves": int(v5.stats[5]), "note": "includes fp16 MLP inference + masked eps-greedy in torch"}
     dt = timed(lambda: adapters.VecCollector(v5, adapters.RandomLegalPolicy(seed=3), buf).collect(), 10)
     out["collect_random_policy"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt}

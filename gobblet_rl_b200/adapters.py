@@ -159,6 +159,20 @@ class VecCollector:
         b = self.buf
         b.obs[0].copy_(b.obs[-1]); b.mask[0].copy_(b.mask[-1]); b.agent_id[0].copy_(b.agent_id[-1])
 
+    def capture(self):
+        """Record one collect() + roll() in a CUDA graph: replaying it removes the per-op launch cost that
+        dominates policy-in-the-loop collection at moderate N.  The policy must be graph-safe (device-side RNG
+        state: torch's generator is; `RandomLegalPolicy(graph_safe_device=...)` keeps its counter on the GPU)."""
+        side = torch.cuda.Stream(device=self.vec.device)
+        side.wait_stream(torch.cuda.current_stream(self.vec.device))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            self.collect(); self.roll()                    # warm-up outside the capture (allocations, lazy init)
+            with torch.cuda.graph(graph, stream=side):
+                self.collect(); self.roll()
+        torch.cuda.current_stream(self.vec.device).wait_stream(side)
+        return graph
+
 
 class RandomLegalPolicy:
     """Uniform over the mask on the GPU (Philox): the vectorised form of example_basic.py:58-61."""

@@ -162,3 +162,26 @@ def test_greedy_vec_policy_self_play_matches_oracle(ad):
         w = o.step(a_np.astype(np.int64))
         assert np.array_equal(obs.cpu().numpy(), w[0]) and np.array_equal(term.cpu().numpy(), w[3])
     assert vec.stats[5] == 0 and vec.stats[0] > 0 and n_fb > 0
+
+
+def test_captured_collection_graph_matches_eager(ad):
+    """VecCollector.capture(): replaying the CUDA graph of collect()+roll() continues the same trajectories
+    as eager collection (device-side Philox counter), checked against an eager twin."""
+    from gobblet_rl_b200 import gobblet_v1
+    n, T = 600, 6
+
+    def make():
+        vec = gobblet_v1.vec_env(n, seed=12)
+        buf = ad.TrajectoryBuffer(T, n, keep_final=False)
+        return vec, buf, ad.VecCollector(vec, ad.RandomLegalPolicy(seed=5, graph_safe_device="cuda"), buf)
+
+    va, ba, ca = make()
+    vb, bb, cb = make()
+    g = ca.capture()                      # runs one eager collect+roll (warm-up), then captures
+    cb.collect(); cb.roll()
+    for _ in range(3):
+        g.replay()
+        cb.collect(); cb.roll()
+        torch.cuda.synchronize()
+        assert torch.equal(ba.act, bb.act) and torch.equal(ba.obs, bb.obs) and torch.equal(ba.rew, bb.rew)
+    assert torch.equal(va.state, vb.state) and va.stats.tolist() == vb.stats.tolist() and va.stats[5] == 0
