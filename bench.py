@@ -269,8 +269,8 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         final = torch.cat([e.state for e in host.envs])
         assert torch.equal(final, logger.state), "host-buffer replay diverged from the fused rollout"
-        e2e = {"value": world * ne * ke / dt.item(), "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes_per_step,
-               "d2h_bytes_per_step": host.d2h_bytes_per_step, "lockstep_steps": ke,
+        e2e = {"value": world * ne * ke / dt.item(), "unit": UNIT, "h2d_bytes_per_step": world * host.h2d_bytes_per_step,
+               "d2h_bytes_per_step": world * host.d2h_bytes_per_step, "lockstep_steps": ke, "envs_per_step": world * ne,
                "api": "HostVecEnv.step(pinned uint8 actions) -> pinned obs/mask/rew/terminated/truncated/agent_id"}
 
     # clocks are sampled over the timed launches (and the e2e steps, which keep the GPU busy too)
