@@ -12,7 +12,7 @@ import warnings
 import numpy as np
 import torch
 
-from . import _aec, _spaces
+from . import _aec, _spaces, ops
 from ._aec import AECEnv, agent_selector
 from .greedy_policy import GreedyGobbletPolicy, greedy_actions  # noqa: F401
 from .vec_env import HostVecEnv, VecEnv  # noqa: F401
@@ -70,7 +70,6 @@ class raw_env(AECEnv):
         self._vec = VecEnv(1, device=device, illegal_mode="pass", autoreset="off")
         self._scratch = None
         self._bind_outputs()
-        self._vec.observe()
         self.board = _BoardView(self)
         self.board_size = 3
         self.agents = ["player_1", "player_2"]
@@ -93,26 +92,45 @@ class raw_env(AECEnv):
         self.screen_width = args.screen_width if hasattr(args, "screen_width") else 640
         self.screen_height = self.screen_width
         self.screen = None
+        self._engine_observe()
+
+    # Batch-of-1 fast path: the action and ALL per-step outputs live in ONE pinned host buffer that the kernels
+    # address directly (UVA zero-copy), and the facade calls the C ABI itself -- a step is one kernel launch and
+    # one stream synchronise, no staging copies and no tensor dispatch.  Layout: obs @0 (117 B) | mask @128 (54 B)
+    # | rew @192 | terminated @194 | truncated @195 | agent_id @196 | action (int64) @208.
+    def _bind_outputs(self):
+        v = self._vec
+        self._hbuf = torch.zeros(256, dtype=torch.uint8).pin_memory()
+        self._host = self._hbuf.numpy()
+        self._host_action = self._host[208:216].view(np.int64)
+        base = self._hbuf.data_ptr()
+        self._ptr = {"obs": base, "mask": base + 128, "rew": base + 192, "term": base + 194, "trunc": base + 195,
+                     "agent": base + 196, "action": base + 208, "state": v.state.data_ptr(), "stats": v.stats.data_ptr()}
+
+    def _finish(self, rc, stream):
+        if rc != 0:
+            raise ops.GobbletError(f"libgobblet_b200 error {rc}: {ops.LIB.gbl_last_error().decode()}")
+        stream.synchronize()
         self._pull()
 
-    # All per-step outputs of the engine land in ONE 256-byte device buffer, so a step costs one kernel launch
-    # and one device->host read: obs @0 (117 B) | mask @128 (54 B) | rew @192 | terminated @194 | truncated
-    # @195 | agent_id @196.
-    def _bind_outputs(self):
-        v, b = self._vec, torch.zeros(256, dtype=torch.uint8, device=self._vec.device)
-        self._buf = b
-        v.obs = b[0:117].view(torch.int8).view(1, 3, 3, 13)
-        v.mask = b[128:182].view(torch.int8).view(1, 54)
-        v.rew = b[192:194].view(torch.int8).view(1, 2)
-        v.terminated = b[194:195].view(torch.bool)
-        v.truncated = b[195:196].view(torch.bool)
-        v.agent_id = b[196:197]
-        self._act = torch.zeros(1, dtype=torch.int64, device=v.device)
+    def _engine_observe(self):
+        p, dev = self._ptr, self._vec.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            self._finish(ops.LIB.gbl_observe(p["state"], p["obs"], p["mask"], p["agent"], 1, stream.cuda_stream), stream)
+
+    def _engine_step(self, action):
+        p, v = self._ptr, self._vec
+        self._host_action[0] = action
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device)
+            self._finish(ops.LIB.gbl_step(p["state"], p["action"], 8, p["obs"], p["mask"], p["rew"], p["term"], p["trunc"],
+                                          p["agent"], None, None, p["stats"], 1, v.flags, stream.cuda_stream), stream)
 
     def _pull(self):
-        host = self._buf.cpu().numpy()
-        self._obs = host[:117].view(np.int8).reshape(3, 3, 13)
-        self._mask = host[128:182].view(np.int8)
+        host = self._host
+        self._obs = host[:117].view(np.int8).reshape(3, 3, 13).copy()
+        self._mask = host[128:182].view(np.int8).copy()
         self._rew = host[192:194].view(np.int8).astype(int)
         self._term = bool(host[194])
         self._sel = int(host[196])
@@ -152,8 +170,7 @@ class raw_env(AECEnv):
     def step(self, action):                                     # gobblet.py:231-273
         if self.terminations[self.agent_selection] or self.truncations[self.agent_selection]:
             return self._was_dead_step(action)
-        self._vec.step(self._act.fill_(int(action)))
-        self._pull()
+        self._engine_step(int(action))
         next_agent = self._agent_selector.next()
         if self._term:
             self.rewards[self.agents[0]] += int(self._rew[0])   # += / -=, zeroed only in reset (:255-260)
@@ -168,8 +185,8 @@ class raw_env(AECEnv):
             self.render()
 
     def reset(self, seed=None, return_info=False, options=None):   # gobblet.py:275-290
-        self._vec.reset()
-        self._pull()
+        ops.reset(self._vec.state, None)
+        self._engine_observe()
         self.agents = self.possible_agents[:]
         self.rewards = {i: 0 for i in self.agents}
         self._cumulative_rewards = {i: 0 for i in self.agents}
