@@ -174,7 +174,7 @@ def main():
                 env.step(np.random.choice(np.arange(len(m)), p=m / np.sum(m)))
                 steps += 1
     out["facade_env_loop"] = {"env_steps_per_s": steps / (time.perf_counter() - t0),
-                              "note": "batch-of-1 AEC facade: one kernel launch + one device->host read per step"}
+                              "note": "batch-of-1 AEC facade: one kernel launch + one stream sync per step (zero-copy pinned buffer), rest is Python"}
     # -- the reference's CPU numbers for the same rows (1 core), when its tree travelled in baseline/_ref ------
     try:
         from oracle import reference_loader as RL
