@@ -1,6 +1,7 @@
 """Multi-GPU sharding: environments are independent, so ranks own contiguous blocks of global env ids
-and exchange NOTHING per step.  The only collective is one end-of-run all-reduce of the int64[8]
-episode statistics (slots 0-6 summed, slot 7 = max episode length maxed) over NCCL (gloo in CPU tests).
+and exchange NOTHING per step.  The only collective is one end-of-run reduction of the int64[8]
+episode statistics (slots 0-6 summed, slot 7 = max episode length maxed): a single 64-byte all-gather over
+NCCL (gloo in CPU tests).
 Because the Philox counters are keyed by GLOBAL env id, any world size plays the same games."""
 import os
 
@@ -32,13 +33,16 @@ def init_from_env(backend=None):
 
 
 def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
-    """Whole-job statistics from per-rank int64[8] vectors (the run's single collective)."""
-    out = stats.clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        sums, mx = out[:7].clone(), out[7:].clone()
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-        out[:7], out[7:] = sums, mx
+    """Whole-job statistics from per-rank int64[8] vectors -- the run's single collective: ONE all-gather of
+    64 bytes per rank (slots 0-6 are summed, slot 7 is a maximum, so a plain SUM all-reduce would not do)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats.clone()
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(parts, stats.contiguous(), group=group)       # works on NCCL and gloo alike
+    gathered = torch.stack(parts)
+    out = gathered.sum(0)
+    out[7] = gathered[:, 7].max()
     return out
 
 
