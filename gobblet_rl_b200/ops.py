@@ -95,10 +95,27 @@ def _need_cuda(*tensors):
     return dev
 
 
+def _need_bytes(name, t: Optional[torch.Tensor], nbytes: int, itemsize: int = 1):
+    """Buffers cross the C ABI as raw pointers: refuse tensors that are too small or of the wrong width."""
+    if t is None:
+        return
+    if t.element_size() != itemsize:
+        raise GobbletError(f"{name}: expected {itemsize}-byte elements, got {t.dtype}")
+    if t.numel() * t.element_size() < nbytes:
+        raise GobbletError(f"{name}: needs {nbytes} bytes, tensor holds {t.numel() * t.element_size()}")
+
+
+def _need_state(state: torch.Tensor):
+    if state.dtype != torch.int64 or state.dim() != 2 or state.shape[1] != 2:
+        raise GobbletError("state must be an int64 [n, 2] tensor (16 bytes per env)")
+    return state.shape[0]
+
+
 # ---- torch custom ops (schema + fake impls so the engine composes with torch.compile / graphs) ------
 @torch.library.custom_op("gobblet_b200::reset", mutates_args=("state",))
 def reset(state: torch.Tensor, which: Optional[torch.Tensor] = None) -> None:
     dev = _need_cuda(state, which)
+    _need_bytes("which", which, _need_state(state))
     with torch.cuda.device(dev):
         _check(LIB.gbl_reset_masked(_ptr(state), _ptr(which), state.shape[0], _stream(state)))
 
@@ -106,6 +123,8 @@ def reset(state: torch.Tensor, which: Optional[torch.Tensor] = None) -> None:
 @torch.library.custom_op("gobblet_b200::observe", mutates_args=("obs", "mask", "agent_id"))
 def observe(state: torch.Tensor, obs: torch.Tensor, mask: torch.Tensor, agent_id: Optional[torch.Tensor]) -> None:
     dev = _need_cuda(state, obs, mask, agent_id)
+    n = _need_state(state)
+    _need_bytes("obs", obs, n * OBS_BYTES); _need_bytes("mask", mask, n * MASK_BYTES); _need_bytes("agent_id", agent_id, n)
     with torch.cuda.device(dev):
         _check(LIB.gbl_observe(_ptr(state), _ptr(obs), _ptr(mask), _ptr(agent_id), state.shape[0], _stream(state)))
 
@@ -117,8 +136,14 @@ def step(state: torch.Tensor, actions: torch.Tensor, obs: torch.Tensor, mask: to
          agent_id: Optional[torch.Tensor], final_obs: Optional[torch.Tensor], final_mask: Optional[torch.Tensor],
          stats: Optional[torch.Tensor], flags: int) -> None:
     dev = _need_cuda(state, actions, obs, mask, rew, terminated, truncated, agent_id, final_obs, final_mask, stats)
-    if actions.dtype not in (torch.uint8, torch.int32, torch.int64) or actions.numel() != state.shape[0]:
+    n = _need_state(state)
+    if actions.dtype not in (torch.uint8, torch.int32, torch.int64) or actions.numel() != n:
         raise GobbletError("actions must be uint8 / int32 / int64 with one entry per env")
+    for name, t, per_env in (("obs", obs, OBS_BYTES), ("mask", mask, MASK_BYTES), ("rew", rew, 2), ("terminated", terminated, 1),
+                             ("truncated", truncated, 1), ("agent_id", agent_id, 1), ("final_obs", final_obs, OBS_BYTES),
+                             ("final_mask", final_mask, MASK_BYTES)):
+        _need_bytes(name, t, n * per_env)
+    _need_bytes("stats", stats, 64, 8)
     with torch.cuda.device(dev):
         _check(LIB.gbl_step(_ptr(state), _ptr(actions), actions.element_size(), _ptr(obs), _ptr(mask), _ptr(rew),
                             _ptr(terminated), _ptr(truncated), _ptr(agent_id), _ptr(final_obs), _ptr(final_mask),
@@ -145,12 +170,20 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
         so, sm = obs_out.stride(0), mask_out.stride(0)          # int8 => element stride == bytes
         if obs_out[0].numel() != n * OBS_BYTES or not obs_out[0].is_contiguous() or not mask_out[0].is_contiguous():
             raise GobbletError("each ring slot must be a contiguous [n,3,3,13] / [n,54] int8 block")
+    _need_state(state)
+    _need_bytes("stats", stats, 64, 8)
+    _need_bytes("step_dev", step_dev, 8, 8)
+    if obs_out is not None and (obs_out.element_size() != 1 or mask_out.element_size() != 1
+                                or mask_out.shape[0] != ring or mask_out[0].numel() != n * MASK_BYTES):
+        raise GobbletError("obs_out / mask_out must be int8 [ring, n, 3, 3, 13] / [ring, n, 54]")
     aux = [t for t in (rew_out, term_out, agent_out) if t is not None]
     if obs_out is None and aux:
         ring = aux[0].shape[0]
     for t in aux:
         if t.shape[0] != ring:
             raise GobbletError("per-step outputs must share one ring length (that of obs_out when it is given)")
+    _need_bytes("rew_out", rew_out, ring * n * 2); _need_bytes("term_out", term_out, ring * n)
+    _need_bytes("agent_out", agent_out, ring * n); _need_bytes("action_log", action_log, T * n)
     with torch.cuda.device(dev):
         _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(step_dev), _ptr(obs_out),
                                       _ptr(mask_out), so, sm, ring, _ptr(rew_out), _ptr(term_out), _ptr(agent_out),
@@ -161,6 +194,8 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
 def sample_legal(mask: torch.Tensor, seed: int, env_id_base: int, step: int, act: torch.Tensor,
                  step_dev: Optional[torch.Tensor] = None) -> None:
     dev = _need_cuda(mask, act, step_dev)
+    _need_bytes("mask", mask, act.numel() * MASK_BYTES); _need_bytes("act", act, 4 * act.numel(), 4)
+    _need_bytes("step_dev", step_dev, 8, 8)
     with torch.cuda.device(dev):
         _check(LIB.gbl_sample_legal(_ptr(mask), seed & (2**64 - 1), env_id_base, step, _ptr(step_dev), _ptr(act),
                                     act.numel(), _stream(mask)))
@@ -171,6 +206,10 @@ def greedy(obs: torch.Tensor, mask: torch.Tensor, prev3: Optional[torch.Tensor],
            ctr_base: int, act: torch.Tensor, chosen: Optional[torch.Tensor], cand: Optional[torch.Tensor],
            used_fallback: Optional[torch.Tensor]) -> None:
     dev = _need_cuda(obs, mask, prev3, act, chosen, cand, used_fallback)
+    n = act.numel()
+    _need_bytes("obs", obs, n * OBS_BYTES); _need_bytes("mask", mask, n * MASK_BYTES); _need_bytes("prev3", prev3, 6 * n, 2)
+    _need_bytes("act", act, 4 * n, 4); _need_bytes("chosen", chosen, 4 * n, 4); _need_bytes("cand", cand, 8 * n, 8)
+    _need_bytes("used_fallback", used_fallback, n)
     with torch.cuda.device(dev):
         _check(LIB.gbl_greedy(_ptr(obs), _ptr(mask), _ptr(prev3), depth, seed & (2**64 - 1), ctr_base, _ptr(act),
                               _ptr(chosen), _ptr(cand), _ptr(used_fallback), act.numel(), _stream(obs)))
@@ -179,6 +218,8 @@ def greedy(obs: torch.Tensor, mask: torch.Tensor, prev3: Optional[torch.Tensor],
 @torch.library.custom_op("gobblet_b200::export_squares", mutates_args=("squares", "agent"))
 def export_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor]) -> None:
     dev = _need_cuda(state, squares, agent)
+    n = _need_state(state)
+    _need_bytes("squares", squares, 27 * n); _need_bytes("agent", agent, n)
     with torch.cuda.device(dev):
         _check(LIB.gbl_export_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
 
@@ -186,6 +227,8 @@ def export_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[t
 @torch.library.custom_op("gobblet_b200::import_squares", mutates_args=("state",))
 def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor]) -> None:
     dev = _need_cuda(state, squares, agent)
+    n = _need_state(state)
+    _need_bytes("squares", squares, 27 * n); _need_bytes("agent", agent, n)
     with torch.cuda.device(dev):
         _check(LIB.gbl_import_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
 

@@ -200,6 +200,17 @@ def test_abi_rejects_bad_arguments(gv1):
                  None, None, None, 3 << 1)                                # bad autoreset mode
     with pytest.raises(ops.GobbletError):
         ops.observe(v.state.cpu(), v.obs, v.mask, None)                  # no CPU path
+    with pytest.raises(ops.GobbletError):
+        ops.observe(v.state, v.obs[:39], v.mask, None)                   # obs too small for 40 envs
+    with pytest.raises(ops.GobbletError):
+        ops.observe(v.state, v.obs.to(torch.int32), v.mask, None)        # wrong element width
+    with pytest.raises(ops.GobbletError):
+        ops.step(v.state, torch.zeros(40, dtype=torch.int64, device="cuda"), v.obs, v.mask, v.rew[:10], None, None,
+                 None, None, None, None, v.flags)                        # rew too small
+    with pytest.raises(ops.GobbletError):
+        ops.greedy(v.obs, v.mask[:20], None, 2, 0, 0, torch.zeros(40, dtype=torch.int32, device="cuda"), None, None, None)
+    with pytest.raises(ops.GobbletError):
+        ops.rollout_random(v.state.view(-1), 1, 0, 0, 0, None, None, None, None, None, None, None, v.flags)   # state shape
 
 
 def test_million_env_properties(gv1):
