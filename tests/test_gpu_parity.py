@@ -315,3 +315,23 @@ def test_empty_mask_and_full_board_greedy_inputs(gv1):
     assert act[1].item() == 5 and act[2].item() in range(54)
     wc, wcand, wfb = O.greedy(_np(obs)[2], _np(mask)[2], (-1, -1, -1), 2)
     assert (chosen[2].item(), bool(fb[2])) == (wc, wfb)
+
+
+def test_custom_ops_trace_under_torch_compile(gv1):
+    """The ops carry schemas with mutated arguments and fake impls, so a caller's step function can be traced
+    (aot_eager: functionalisation + fake tensors, no code generation) with the engine call inside the graph."""
+    from gobblet_rl_b200 import ops
+    v = gv1.vec_env(256, seed=3, autoreset="off")
+    ref = gv1.vec_env(256, seed=3, autoreset="off")
+
+    def fn(state, actions, obs, mask, rew, term, trunc, agent, stats):
+        ops.step(state, actions, obs, mask, rew, term, trunc, agent, None, None, stats, v.flags)
+        return obs.sum(dim=(1, 2, 3)) + mask.sum(dim=1)
+
+    compiled = torch.compile(fn, backend="aot_eager", fullgraph=True)
+    acts = torch.full((256,), 4, dtype=torch.int64, device="cuda")
+    got = compiled(v.state, acts, v.obs, v.mask, v.rew, v.terminated.view(torch.uint8), v.truncated.view(torch.uint8),
+                   v.agent_id, v.stats)
+    want_obs, want_mask, *_ = ref.step(acts)
+    assert torch.equal(v.obs, want_obs) and torch.equal(v.mask, want_mask) and torch.equal(v.state, ref.state)
+    assert torch.equal(got, want_obs.sum(dim=(1, 2, 3)) + want_mask.sum(dim=1))
