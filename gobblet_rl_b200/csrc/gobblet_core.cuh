@@ -253,12 +253,15 @@ __device__ __forceinline__ uint32_t sample_action(uint32_t m0, uint32_t m1, uint
 // contiguous mask bytes (both multiples of 16), staged per warp in shared memory:
 //   * observation: the image is the FINAL byte layout (byte lane*117 + pos*13 + c, gobblet.py:188-208).
 //     It is kept all-zero between steps; each lane SCATTERS the <= 12 one-bytes of its pieces (one FLO
-//     + one IMAD + one predicated STS.U8 per piece) and, for player_2, the 9 bytes of plane 12; the
-//     warp then copies the image out with 128-bit loads / stores, zeroing it behind itself.
+//     + one IMAD + one predicated STS.U8 per piece) and, for player_2, the 9 bytes of plane 12; one lane
+//     then hands the whole image to the copy engine (TMA bulk store) while the warp expands the mask, and
+//     the warp re-zeroes the image once the engine has read it.
 //   * mask: each lane shifts its 54-bit mask to its bit offset in the warp's packed stream (boundary
 //     words merged with one shuffle); every lane then turns 16 stream bits into 16 bytes
 //     (nibble * 0x00204081 & 0x01010101).
-// Every global store is a full 128-bit, fully coalesced STG: 234 + 108 per warp and step.
+// Per warp and step: one 3744-byte bulk store + 108 full 128-bit, fully coalesced STG for the mask
+// (234 + 108 STG with -DGBL_BULK_STORE=0 and in the ragged last warp).
+// Protocol: stage_env | __syncwarp | emit_chunk | __syncwarp, repeated; see the comments of both.
 constexpr int OBS_IMG_BYTES = 32 * 117, MASK_WORDS = 54;
 constexpr int STAGE_BYTES = OBS_IMG_BYTES + 4 * MASK_WORDS + 8;  // 3968, multiple of 16
 constexpr int OBS_VEC = 234, MASK_VEC = 108;                    // uint4 stores per warp
