@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--plain-stores", action="store_true", help="st.global instead of st.global.cs")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local cores")
     return ap.parse_args()
 
 
@@ -210,6 +211,7 @@ def main():
     rank, local, world = sharding.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa_bound = False if a.no_numa_bind else sharding.bind_to_gpu_numa_node(local)
     n, T = a.envs_per_gpu, a.fused_steps
     ring = a.ring if a.ring > 0 else T
     vec = gobblet_v1.vec_env(n, device=dev, seed=0, env_id_base=rank * n, streaming_stores=not a.plain_stores)
@@ -270,7 +272,7 @@ def main():
         final = torch.cat([e.state for e in host.envs])
         assert torch.equal(final, logger.state), "host-buffer replay diverged from the fused rollout"
         e2e = {"value": world * ne * ke / dt.item(), "unit": UNIT, "h2d_bytes_per_step": world * host.h2d_bytes_per_step,
-               "d2h_bytes_per_step": world * host.d2h_bytes_per_step, "lockstep_steps": ke, "envs_per_step": world * ne,
+               "d2h_bytes_per_step": world * host.d2h_bytes_per_step, "lockstep_steps": ke, "envs_per_step": world * ne, "numa_bound": numa_bound,
                "api": "HostVecEnv.step(pinned uint8 actions) -> pinned obs/mask/rew/terminated/truncated/agent_id"}
 
     # clocks are sampled over the timed launches (and the e2e steps, which keep the GPU busy too)

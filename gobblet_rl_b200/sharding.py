@@ -32,6 +32,21 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin this process to the CPU cores NVML reports as local to the GPU, so that pinned host buffers allocated
+    afterwards (first touch) live on the GPU's NUMA node -- matters for the host-buffer path (`HostVecEnv`) when
+    several ranks stream 50 GB/s each over PCIe.  Returns False when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device_index]) if visible and visible.replace(",", "").isdigit() else device_index
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
+
+
 def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """Whole-job statistics from per-rank int64[8] vectors -- the run's single collective: ONE all-gather of
     64 bytes per rank (slots 0-6 are summed, slot 7 is a maximum, so a plain SUM all-reduce would not do)."""
