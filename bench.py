@@ -317,10 +317,37 @@ def main():
     # ---- CPU side by side (rank 0, N=1 only): bounded samples on the host cores ---------------------------
     cpu = None
     if world == 1 and not a.no_cpu:
+        # parity gate: the throughput above is only reported for a build whose logged
+        # actions replay bit-exactly through the CPU checker (and through the reference itself when present)
+        gate = gobblet_v1.vec_env(512, device=dev, seed=99)
+        got = gate.rollout_random(24, ring=24, per_step=True, log_actions=True)
+        from oracle import oracle as O
+        from oracle import reference_loader as RL
+        ora = O.VecOracle(512)
+        want = ora.rollout_random(24, seed=99)
+        for key in ("actions", "obs", "mask", "rew", "terminated", "agent_id"):
+            assert (got[key].cpu().numpy() == want[key]).all(), f"parity gate failed on {key}"
+        assert gate.stats.tolist() == ora.stats.tolist(), "parity gate failed on statistics"
+        parity = "512 envs x 24 fused steps bit-exact vs oracle (obs, mask, rew, terminated, agent_id, actions, stats)"
+        if RL.available():
+            gob = RL.load_gobblet()
+            acts = got["actions"].cpu().numpy()
+            for e_i in range(0, 512, 128):
+                env = gob.raw_env(render_mode=None)
+                env.reset()
+                for t in range(24):
+                    env.step(int(acts[t, e_i]))
+                    if env.terminations[env.agent_selection]:
+                        env.reset()
+                    o = env.observe(env.agent_selection)
+                    assert (o["observation"] == want["obs"][t, e_i]).all() and (o["action_mask"] == want["mask"][t, e_i]).all(), \
+                        "parity gate failed against the reference"
+            parity += "; 4 envs replayed through the unmodified reference"
         kind = reference_kind()
         rate1, s1_, w1_ = cpu_rate(kind, 1, 10.0)
         cpu = {"value": rate1, "unit": UNIT, "cores": 1, "kind": kind,
-               "sample": f"{s1_} live steps in {w1_:.1f}s of the example_basic.py:50-67 loop, 1 process"}
+               "sample": f"{s1_} live steps in {w1_:.1f}s of the example_basic.py:50-67 loop, 1 process",
+               "parity_gate": parity}
         if kind == "reference":
             pr, ps, pw = cpu_rate("port", 1, 4.0)
             cpu["port"] = {"value": pr, "unit": UNIT, "cores": 1, "kind": "port",
