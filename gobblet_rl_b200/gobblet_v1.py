@@ -30,6 +30,14 @@ def env(render_mode=None, args=None, device="cuda"):
     return e
 
 
+class ManualGobbletPolicy:
+    """Name kept for import compatibility (gobblet_rl/gobblet_v1.py:3).  The reference's class is a pygame
+    mouse / keyboard UI (manual_policy.py); interactive play is out of scope of the batched engine."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("ManualGobbletPolicy is a pygame UI in the reference; not part of the B200 engine")
+
+
 def parallel_env(**kwargs):
     raise NotImplementedError("gobblet is turn based; the reference skips the parallel API too "
                               "(tests/test_gobblet_env.py:37-42)")
