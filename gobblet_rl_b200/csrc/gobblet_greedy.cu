@@ -126,28 +126,47 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
 
     // ---- depth 2 (greedy_policy.py:103-157): loop roots, replies in lanes -------------------------
     if (depth > 1) {
+        // The opponent's legal replies after each root move (greedy_policy.py:110-114) do not depend on the
+        // lane, so computing them inside the root loop would repeat ~45 instructions on all 32 lanes per root.
+        // Each lane computes them for "its" two roots instead (lane, lane+32) and the loop broadcasts them.
+        uint32_t rep_lo[2], rep_hi[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t a = lane + 32u * r;
+            rep_lo[r] = rep_hi[r] = 0;
+            if ((roots >> a) & 1ull) {
+                uint32_t x1 = xo, y1 = yo;
+                apply_xy(x1, y1, a);
+                uint32_t occ = x1 | y1 | xp | yp, u1 = occ | (occ >> 9) | (occ >> 18);
+                legal_mask(xp, yp, u1, u1 >> 9, rep_lo[r], rep_hi[r]);
+            }
+        }
         for (; roots; roots &= roots - 1) {
             const int a = __ffsll((long long)roots) - 1;
             uint32_t x1 = xo, y1 = yo;
             apply_xy(x1, y1, (uint32_t)a);
-            uint32_t occ = x1 | y1 | xp | yp, u1 = occ | (occ >> 9) | (occ >> 18), r0, r1;
-            legal_mask(xp, yp, u1, u1 >> 9, r0, r1);                     // opponent's legal replies (:110-114)
+            const uint32_t r0 = __shfl_sync(FULL, a < 32 ? rep_lo[0] : rep_lo[1], a & 31);
+            const uint32_t r1 = __shfl_sync(FULL, a < 32 ? rep_hi[0] : rep_hi[1], a & 31);
             const uint64_t replies = (uint64_t)r0 | ((uint64_t)r1 << 32);
-            bool theirs[2], notmine[2];
+            uint32_t theirs[2] = {0u, 0u}, notmine[2] = {0u, 0u};     // ballots of the two rounds of 32 replies
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                uint32_t a2 = lane + 32u * r;
+                const uint32_t a2 = lane + 32u * r;
                 int w = 1;
-                if ((replies >> a2) & 1ull) {
+                const bool is_reply = (replies >> a2) & 1ull;
+                if (is_reply) {
                     uint32_t x2 = xp, y2 = yp;
                     apply_xy(x2, y2, a2);
                     w = winner_of(lut, x1, y1, x2, y2);
-                } else a2 = 64u;
-                theirs[r] = a2 < 64u && w < 0;
-                notmine[r] = a2 < 64u && w <= 0;
+                }
+                theirs[r] = __ballot_sync(FULL, is_reply && w < 0);
+                notmine[r] = __ballot_sync(FULL, is_reply && w <= 0);
+                // once a move has been chosen only "can the opponent win at all" matters for this root (the block
+                // move of :141-143 needs `chosen is None`), so a hit in the first round settles it
+                if (r == 0 && chosen >= 0 && theirs[0]) break;
             }
-            const uint64_t W = ballot64(theirs[0], theirs[1]);            // replies that win for the opponent
-            const bool all_mine = ballot64(notmine[0], notmine[1]) == 0;  // vacuously true without replies
+            const uint64_t W = (uint64_t)theirs[0] | ((uint64_t)theirs[1] << 32);   // replies that win for the opponent
+            const bool all_mine = (notmine[0] | notmine[1]) == 0;                    // vacuously true without replies
             if (W) {
                 if (ncand > 1) {                                          // :131-136
                     if ((cand >> a) & 1ull) { cand &= ~(1ull << a); --ncand; }
