@@ -13,6 +13,9 @@ namespace gbl {
 #ifndef GBL_BLOCK
 #define GBL_BLOCK 256   // threads per block (tuning knob; 256 measured best on B200)
 #endif
+#ifndef GBL_STEP_MIN_BLOCKS
+#define GBL_STEP_MIN_BLOCKS (1024 / GBL_BLOCK)   // resident blocks per SM requested for step_kernel
+#endif
 constexpr int BLOCK = GBL_BLOCK, WARPS = BLOCK / 32, MIN_BLOCKS = 1024 / BLOCK;
 
 // ---- block-level statistics reduction: shuffles -> shared -> one atomic per slot per block ----
@@ -82,7 +85,7 @@ struct StepParams {
 };
 
 template <typename ActT, bool kStreaming>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) step_kernel(StepParams p) {
+__global__ void __launch_bounds__(BLOCK, GBL_STEP_MIN_BLOCKS) step_kernel(StepParams p) {
     __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
