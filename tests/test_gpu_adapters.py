@@ -185,3 +185,27 @@ def test_captured_collection_graph_matches_eager(ad):
         torch.cuda.synchronize()
         assert torch.equal(ba.act, bb.act) and torch.equal(ba.obs, bb.obs) and torch.equal(ba.rew, bb.rew)
     assert torch.equal(va.state, vb.state) and va.stats.tolist() == vb.stats.tolist() and va.stats[5] == 0
+
+
+def test_host_vec_env_matches_oracle(ad):
+    """The host-buffer path bench.py reports as `e2e`: pinned actions in, pinned obs / mask / rew / flags out,
+    chunked over CUDA streams -- same results as the oracle, whatever the chunking."""
+    from gobblet_rl_b200 import gobblet_v1
+    n, T = 1003, 25
+    host = gobblet_v1.HostVecEnv(n, chunks=5, seed=0, autoreset="same_step")
+    o = O.VecOracle(n, "terminate", "same_step")
+    obs, mask, agent = host.reset()
+    wobs, wmask, wagent = o.reset()
+    assert np.array_equal(obs.numpy(), wobs) and np.array_equal(mask.numpy(), wmask)
+    rng = np.random.default_rng(2)
+    acts = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for t in range(T):
+        a = np.array([rng.choice(np.flatnonzero(m)) for m in wmask], np.int64)
+        a[rng.random(n) < 0.05] = 60                                  # some illegal moves
+        acts.copy_(torch.as_tensor(a, dtype=torch.uint8))
+        got = host.step(acts)
+        w = o.step(a)
+        for g, ww in zip(got, w):
+            assert np.array_equal(g.numpy(), ww), t
+        wmask = w[1]
+    assert host.h2d_bytes_per_step == n and host.d2h_bytes_per_step == n * 176
