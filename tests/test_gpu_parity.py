@@ -335,3 +335,50 @@ def test_custom_ops_trace_under_torch_compile(gv1):
     want_obs, want_mask, *_ = ref.step(acts)
     assert torch.equal(v.obs, want_obs) and torch.equal(v.mask, want_mask) and torch.equal(v.state, ref.state)
     assert torch.equal(got, want_obs.sum(dim=(1, 2, 3)) + want_mask.sum(dim=1))
+
+
+def _random_boards(rng, n):
+    """Arbitrary (not necessarily reachable) placements: every piece in hand or on a random square, at most one
+    piece per (level, square) cell -- stresses covered pieces, double lines and full columns."""
+    sq = np.zeros((n, 27), np.int8)
+    for i in range(n):
+        for sign in (1, -1):
+            for k in range(1, 7):
+                if rng.random() < 0.7:
+                    lvl = (k - 1) // 2
+                    free = np.flatnonzero(sq[i, 9 * lvl: 9 * lvl + 9] == 0)
+                    if len(free):
+                        sq[i, 9 * lvl + rng.choice(free)] = sign * k
+    return sq
+
+
+def test_synthetic_positions_observe_step_and_greedy(gv1):
+    rng = np.random.default_rng(11)
+    n = 3000
+    sq = _random_boards(rng, n)
+    agent = rng.integers(0, 2, n).astype(np.uint8)
+    v = gv1.vec_env(n, illegal_mode="pass", autoreset="off")
+    o = O.VecOracle(n, "pass", "off")
+    obs, mask, ag = v.set_squares(sq, agent)
+    o.set(sq, agent)
+    wobs, wmask, wag = o.observe()
+    assert np.array_equal(_np(obs), wobs) and np.array_equal(_np(mask), wmask) and np.array_equal(_np(ag), wag)
+    # greedy on these positions, with masks that are sometimes INCONSISTENT with the board (random extra / missing bits)
+    gmask = wmask.copy()
+    flip = rng.random(gmask.shape) < 0.05
+    gmask[flip] ^= 1
+    gmask[gmask.sum(1) == 0, 0] = 1
+    prev3 = rng.integers(-1, 54, (n, 3)).astype(np.int16)
+    for depth in (1, 2):
+        act, chosen, cand, fb = gv1.greedy_actions(obs, torch.as_tensor(gmask).cuda(), torch.as_tensor(prev3), depth=depth, details=True)
+        chosen, cand, fb = _np(chosen), _np(cand).astype(np.uint64), _np(fb)
+        for i in range(n):
+            wc, wcand, wfb = O.greedy(wobs[i], gmask[i], prev3[i], depth)
+            assert (int(chosen[i]), int(cand[i]), bool(fb[i])) == (wc, sum(1 << a for a in wcand), wfb), (depth, i)
+    # one step with arbitrary actions from these positions (winner by line order, uncovering, illegal = pass)
+    acts = rng.integers(0, 54, n)
+    g = v.step(torch.as_tensor(acts).cuda())
+    w = o.step(acts)
+    for i in range(6):
+        assert np.array_equal(_np(g[i]), w[i]), i
+    assert np.array_equal(_np(v.squares()[0]), o.squares())
