@@ -182,13 +182,13 @@ __device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1,
             }
         }
     }
-    int w = 0; bool both = false;
-    if (legal) {
-        apply_move(e, action);
-        uint32_t u, up;
-        occupancy(e, u, up);
-        w = winner_rel(tops(e.xo, e.yo, up), tops(e.xp, e.yp, up), both);
-    }
+    // play_turn is a no-op for an illegal move (board.py:125-126), but check_game_over still runs on the
+    // board as it is (gobblet.py:248) -- observable on imported positions that already hold a line
+    if (legal) apply_move(e, action);
+    bool both = false;
+    uint32_t u, up;
+    occupancy(e, u, up);
+    const int w = winner_rel(tops(e.xo, e.yo, up), tops(e.xp, e.yp, up), both);
     pass_turn(e);
     e.plies++;
     // gobblet.py:248-263, branch-free: the winner is the mover when w > 0, the other player when w < 0
