@@ -1,6 +1,6 @@
 // Host emulation of the rollout / step kernel bodies of gobblet_engine.cu, built from the SAME
-// gobblet_core.cuh device functions (TEST ONLY).  One "warp" = 32 lanes run in lockstep; the two
-// shuffle of stage_env is emulated with a record/replay pass.
+// gobblet_core.cuh device functions (TEST ONLY).  One "warp" = 32 lanes run in lockstep; the
+// one shuffle of stage_env is emulated with a record/replay pass.
 #include "cuda_shim.h"
 #include "../../include/gobblet_b200.h"
 #include "../../gobblet_rl_b200/csrc/gobblet_core.cuh"
