@@ -256,7 +256,7 @@ def main():
         log = logger.rollout_random(ke + we, emit=False, log_actions=True)["actions"]
         h_log = torch.zeros(log.shape, dtype=torch.uint8, pin_memory=True)
         h_log.copy_(log)
-        host = gobblet_v1.HostVecEnv(ne, device=dev, chunks=8, seed=1, env_id_base=rank * ne)
+        host = gobblet_v1.HostVecEnv(ne, device=dev, chunks=2, seed=1, env_id_base=rank * ne)
         host.reset()
         for k in range(we):
             host.step(h_log[k])

@@ -168,7 +168,7 @@ class HostVecEnv:
     copies chunked over CUDA streams so PCIe transfers overlap the kernels.  This is the end-to-end
     path `bench.py` reports as `e2e` (what a CPU-side PettingZoo/Tianshou driver would see)."""
 
-    def __init__(self, num_envs, device="cuda", chunks=4, **kw):
+    def __init__(self, num_envs, device="cuda", chunks=2, **kw):
         self.device = torch.device(device)
         self.num_envs = int(num_envs)
         bounds = [self.num_envs * i // chunks for i in range(chunks + 1)]
