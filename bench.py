@@ -283,6 +283,21 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- same-run write-only reference: a plain fill of the same trajectory buffer ---------
+    ring_obs, ring_mask = vec._rings[1], vec._rings[2]
+    flat = ring_obs.reshape(-1) if ring_obs.is_contiguous() else ring_obs[0].reshape(-1)
+    flat = flat[: flat.numel() // 16 * 16].view(torch.int64)          # 8-byte elements: the fill kernel's widest stores
+    for _ in range(2):
+        flat.fill_(0)
+    torch.cuda.synchronize(dev)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(5):
+        flat.fill_(0)
+    f1.record()
+    torch.cuda.synchronize(dev)
+    fill_gbs = 5 * flat.numel() * 8 / (f0.elapsed_time(f1) * 1e-3) / 1e9
+
     # ---- roofline of the fused rollout kernel -----------------------------------------------------------
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -300,7 +315,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "gbl::rollout_kernel<true,true,false>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
-                "launch_ms_avg": launch_ms, "launch_ms_min": per_launch[0], "launch_ms_median": per_launch[len(per_launch) // 2]}
+                "launch_ms_avg": launch_ms, "launch_ms_min": per_launch[0], "launch_ms_median": per_launch[len(per_launch) // 2],
+                "same_run_fill_gbs": fill_gbs, "frac_of_same_run_fill": achieved / fill_gbs,
+                "fill_note": f"torch fill_ (int64 view) of the {flat.numel() * 8 / 1e9:.1f} GB observation trajectory buffer, write-only"}
 
     # ---- config 2 (4096 envs): latency-bound, reported beside the headline --------------------------------
     small = gobblet_v1.vec_env(4096, device=dev, seed=0)

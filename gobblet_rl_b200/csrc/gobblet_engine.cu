@@ -16,11 +16,16 @@ namespace gbl {
 #ifndef GBL_STEP_MIN_BLOCKS
 #define GBL_STEP_MIN_BLOCKS (1024 / GBL_BLOCK)   // resident blocks per SM requested for step_kernel
 #endif
+#ifndef GBL_ROLLOUT_BLOCK
+#define GBL_ROLLOUT_BLOCK GBL_BLOCK   // threads per block of the fused rollout kernel (dynamic shared memory)
+#endif
 constexpr int BLOCK = GBL_BLOCK, WARPS = BLOCK / 32, MIN_BLOCKS = 1024 / BLOCK;
+constexpr int RBLOCK = GBL_ROLLOUT_BLOCK, RWARPS = RBLOCK / 32, RMIN_BLOCKS = 1024 / RBLOCK;
 
 // ---- block-level statistics reduction: shuffles -> shared -> one atomic per slot per block ----
+template <int NW = WARPS>
 __device__ __forceinline__ void flush_stats(const Stats &st, bool valid, int64_t *stats) {
-    __shared__ uint32_t red[WARPS][8];
+    __shared__ uint32_t red[NW][8];
     uint32_t v[8] = {st.episodes, st.p1w, st.p2w, st.steps, st.sumlen, st.illegal, st.both, st.maxlen};
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -32,7 +37,7 @@ __device__ __forceinline__ void flush_stats(const Stats &st, bool valid, int64_t
     __syncthreads();
     if (threadIdx.x < 8) {
         unsigned long long acc = 0;
-        for (int w = 0; w < WARPS; ++w)
+        for (int w = 0; w < NW; ++w)
             acc = threadIdx.x == 7 ? max(acc, (unsigned long long)red[w][7]) : acc + red[w][threadIdx.x];
         if (acc) {
             if (threadIdx.x == 7) atomicMax(reinterpret_cast<long long *>(stats) + 7, (long long)acc);
@@ -160,10 +165,11 @@ struct RolloutParams {
 
 // kAux: any of rew_out / term_out / agent_out / action_log is requested (compiled out otherwise)
 template <bool kFast, bool kStreaming, bool kAux>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) rollout_kernel(RolloutParams p) {
-    __shared__ __align__(16) uint8_t stage[WARPS][STAGE_BYTES];
+__global__ void __launch_bounds__(RBLOCK, RMIN_BLOCKS) rollout_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) uint8_t stage_all[];      // RWARPS * STAGE_BYTES, one staging area per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
+    const int64_t g = (int64_t)blockIdx.x * RBLOCK + threadIdx.x, first = g - lane;
+    uint8_t *const stage = stage_all + warp * STAGE_BYTES;
     const bool valid = g < p.n;
     Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
     if (first < p.n) {
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) rollout_kernel(RolloutParam
         uint32_t u, up, m0, m1;
         occupancy(e, u, up);
         legal_mask(e.xo, e.yo, u, up, m0, m1);
-        stage_init(stage[warp], lane);
+        stage_init(stage, lane);
         __syncwarp();
         const uint64_t step_base = p.step_base_dev ? *p.step_base_dev : p.step_base;
         uint4 rnd = make_uint4(0, 0, 0, 0);
@@ -201,9 +207,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) rollout_kernel(RolloutParam
                 if (p.action_log) p.action_log[(int64_t)t * p.n + g] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
             if (emit) {
-                stage_env(stage[warp], cfg, lane, e, m0, m1);
+                stage_env(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(stage[warp], lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
+                emit_chunk<kStreaming>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
                                        p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid);
                 __syncwarp();
             }
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) rollout_kernel(RolloutParam
             st.p2w = st.episodes - st.p1w;
         }
     }
-    if (p.stats) flush_stats(st, valid, p.stats);
+    if (p.stats) flush_stats<RWARPS>(st, valid, p.stats);
 }
 
 // ---- masked-uniform sampler over int8 masks -----------------------------------------------------
@@ -371,12 +377,19 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     const bool fast = (flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_SAME_STEP;
     const bool plain = flags & GBL_STORE_DEFAULT_POLICY;
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned grid = grid_for(n);
+    const unsigned grid = (unsigned)((n + RBLOCK - 1) / RBLOCK);
+    const size_t smem = (size_t)RWARPS * STAGE_BYTES;
     const bool aux = rew_out || term_out || agent_out || action_log;
+#define GBL_LAUNCH_ROLLOUT_1(F, S, A)                                                                            \
+    do {                                                                                                         \
+        if (smem > 48 * 1024)                                                                                    \
+            cudaFuncSetAttribute(rollout_kernel<F, S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        rollout_kernel<F, S, A><<<grid, RBLOCK, smem, s>>>(p);                                                   \
+    } while (0)
 #define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
     do {                                                                            \
-        if (aux) rollout_kernel<F, S, true><<<grid, BLOCK, 0, s>>>(p);              \
-        else rollout_kernel<F, S, false><<<grid, BLOCK, 0, s>>>(p);                 \
+        if (aux) GBL_LAUNCH_ROLLOUT_1(F, S, true);                                  \
+        else GBL_LAUNCH_ROLLOUT_1(F, S, false);                                     \
     } while (0)
     if (fast) {
         if (plain) GBL_LAUNCH_ROLLOUT(true, false);
@@ -386,6 +399,7 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
         else GBL_LAUNCH_ROLLOUT(false, true);
     }
 #undef GBL_LAUNCH_ROLLOUT
+#undef GBL_LAUNCH_ROLLOUT_1
     return check_launch("gbl_rollout_random");
 }
 
