@@ -382,13 +382,13 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
 // warp that exist (32 except in the last warp).
 template <bool kStreaming>
 __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t *obs_chunk,
-                                           int8_t *mask_chunk, int nvalid) {
+                                           int8_t *mask_chunk, int nvalid, uint32_t skip = 0u) {
     uint4 *img = reinterpret_cast<uint4 *>(stage);
     const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage + OBS_IMG_BYTES);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid == 32) {
         if (kBulkStore) {
-            if (lane == 0) bulk_store_issue(obs_chunk, stage, OBS_IMG_BYTES);
+            if (lane == 0 && !(skip & 1u)) bulk_store_issue(obs_chunk, stage, OBS_IMG_BYTES);
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -403,7 +403,7 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint32_t q = lane + 32u * i;
-            if (i < 3 || q < MASK_VEC) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
+            if ((i < 3 || q < MASK_VEC) && !(skip & 2u)) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
         }
         if (kBulkStore) {                      // re-zero the image once the copy engine has read it
             if (lane == 0) bulk_store_wait_read();

@@ -19,7 +19,7 @@ namespace gbl {
 #ifndef GBL_ROLLOUT_BLOCK
 #define GBL_ROLLOUT_BLOCK GBL_BLOCK   // threads per block of the fused rollout kernel (dynamic shared memory)
 #endif
-constexpr int BLOCK = GBL_BLOCK, WARPS = BLOCK / 32, MIN_BLOCKS = 1024 / BLOCK;
+constexpr int BLOCK = GBL_BLOCK, WARPS = BLOCK / 32;
 constexpr int RBLOCK = GBL_ROLLOUT_BLOCK, RWARPS = RBLOCK / 32, RMIN_BLOCKS = 1024 / RBLOCK;
 
 // ---- block-level statistics reduction: shuffles -> shared -> one atomic per slot per block ----
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(RBLOCK, RMIN_BLOCKS) rollout_kernel(RolloutPar
                 stage_env(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
                 emit_chunk<kStreaming>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
-                                       p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid);
+                                       p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid,
+                                       (p.flags >> 8) & 3u);   // GBL_MEASURE_SKIP_*_STORES
                 __syncwarp();
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;

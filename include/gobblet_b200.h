@@ -57,6 +57,8 @@ extern "C" {
 #define GBL_AUTORESET_NEXT_STEP (2u << 1)
 #define GBL_AUTORESET_MASK (3u << 1)
 #define GBL_ACTION_SKIP_255 0x10u     /* gbl_step: action 255 leaves that env untouched (Tianshou steps a SUBSET of env ids) */
+#define GBL_MEASURE_SKIP_OBS_STORES 0x100u  /* gbl_rollout_random only: measurement aid, do everything but the obs stores */
+#define GBL_MEASURE_SKIP_MASK_STORES 0x200u /* gbl_rollout_random only: measurement aid, do everything but the mask stores */
 #define GBL_STORE_DEFAULT_POLICY 0x8u /* use plain st.global instead of streaming (evict-first) stores */
 
 /* errors */
