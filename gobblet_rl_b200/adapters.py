@@ -80,6 +80,11 @@ class PettingZooVecEnv:
         """PettingZooEnv.step for the envs in `id` (all when None): env.step(a); env.last()."""
         v = self.vec
         ids = self._ids(id)
+        if not (torch.is_tensor(action) and action.is_cuda):
+            # AssertOutOfBoundsWrapper (gobblet.py:115): an action outside Discrete(54) raises.  Host-side actions
+            # are checked here; CUDA tensors are not read back -- the kernel treats out-of-range as an illegal move.
+            a_host = np.asarray(action.cpu() if torch.is_tensor(action) else action).reshape(-1)
+            assert ((a_host >= 0) & (a_host < 54)).all(), "action is not in action space"
         act = torch.as_tensor(np.asarray(action) if not torch.is_tensor(action) else action, device=v.device).long().reshape(-1)
         if ids is None:
             full = act
@@ -138,13 +143,27 @@ class VecCollector:
     `policy(obs[N,3,3,13], mask[N,54], agent_id[N]) -> actions[N]` (example_tianshou_DQN.py:401-409 shape).
     Same-step auto-reset + final observation capture = Tianshou's reset-after-done ordering in one launch."""
 
-    def __init__(self, vec: VecEnv, policy, buffer: TrajectoryBuffer):
+    def __init__(self, vec: VecEnv, policy, buffer: TrajectoryBuffer, fused: bool = True):
         assert vec.autoreset == "same_step", "VecCollector drives a same-step auto-reset VecEnv"
         self.vec, self.policy, self.buf = vec, policy, buffer
+        # the built-in masked-uniform policy is the sampler of the fused rollout kernel: the whole collection
+        # (sample -> step -> emit, T times) is then ONE launch writing straight into the buffer slots
+        self.fused = bool(fused) and type(policy) is RandomLegalPolicy
         obs, mask, agent = vec.observe()
         buffer.obs[0].copy_(obs); buffer.mask[0].copy_(mask); buffer.agent_id[0].copy_(agent)
 
+    def _collect_fused(self):
+        b, v, p = self.buf, self.vec, self.policy
+        ops.rollout_random(v.state, b.horizon, p.seed, p.env_id_base, p.step, b.obs[1:], b.mask[1:], b.rew,
+                           b.terminated.view(torch.uint8), b.agent_id[1:], b.act, v.stats, v.flags | ops.SLOT_FROM_ZERO,
+                           p.step_dev, b.final_obs, b.final_mask)
+        v._advance(b.horizon)
+        p.advance(b.horizon)
+        return b
+
     def collect(self):
+        if self.fused:
+            return self._collect_fused()
         b, v = self.buf, self.vec
         for t in range(b.horizon):
             act = self.policy(b.obs[t], b.mask[t], b.agent_id[t])
@@ -184,11 +203,15 @@ class RandomLegalPolicy:
 
     def __call__(self, obs, mask, agent_id=None):
         act = torch.empty(mask.shape[0], dtype=torch.int32, device=mask.device)
-        ops.sample_legal(mask.to(torch.int8).contiguous(), self.seed, self.env_id_base, self.step, act, self.step_dev)
-        if self.step_dev is not None:
-            self.step_dev += 1
-        self.step += 1
+        m = mask if mask.dtype in (torch.int8, torch.uint8, torch.bool) and mask.is_contiguous() else mask.to(torch.int8).contiguous()
+        ops.sample_legal(m, self.seed, self.env_id_base, self.step, act, self.step_dev)
+        self.advance(1)
         return act
+
+    def advance(self, steps: int):
+        if self.step_dev is not None:
+            self.step_dev += int(steps)
+        self.step += int(steps)
 
 
 class GreedyVecPolicy:

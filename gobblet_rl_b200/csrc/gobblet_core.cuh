@@ -144,6 +144,7 @@ struct StepResult {
     int r1, r2;       // env.rewards[player_1], [player_2]
     bool term, trunc; // flags of THIS step
     bool acted;       // an action was consumed (false for dead envs / reset-only / skipped steps)
+    bool skipped;     // GBL_ACTION_SKIP_255: the env was not in the stepped subset (never reset)
 };
 
 // (m0, m1) = legal mask of the mover BEFORE the move.  kFast drops the paths a random-legal rollout
@@ -152,10 +153,10 @@ struct StepResult {
 template <bool kFast>
 __device__ __forceinline__ StepResult env_step(Env &e, uint32_t m0, uint32_t m1, uint32_t action,
                                                uint32_t flags, Stats &st) {
-    StepResult r = {0, 0, false, false, true};
+    StepResult r = {0, 0, false, false, true, false};
     const uint32_t autoreset = (flags >> 1) & 3u;
     if (!kFast && (flags & 0x10u) && action == 255u) {   // GBL_ACTION_SKIP_255: env not in the stepped subset
-        r.acted = false;
+        r.acted = false; r.skipped = true;
         r.term = e.done != 0; r.trunc = e.trunc != 0;
         return r;
     }
@@ -349,6 +350,11 @@ __device__ __forceinline__ void bulk_store_wait_all() {    // the global writes 
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif
 }
+__device__ __forceinline__ void bulk_store_wait_all_but_latest() {   // every group but the newest has completed
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void fence_smem_for_bulk() {    // generic-proxy smem writes -> visible to the copy engine
 #ifdef __CUDA_ARCH__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -379,16 +385,26 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
 }
 
 // copy / expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this
-// warp that exist (32 except in the last warp).
+// warp that exist (32 except in the last warp).  opts: bit 0 / 1 = GBL_MEASURE_SKIP_OBS / MASK_STORES;
+// EMIT_REUSE_RING / EMIT_REUSE_ALWAYS = the same global slot is written again later in this launch (ring < T):
+// PTX orders separate bulk async-groups only through wait_group, so the store that last targeted this slot
+// must have COMPLETED (not merely been read) before the next one is issued -- that is the group before the
+// newest one when ring >= 2, the newest one when ring == 1.
+constexpr uint32_t EMIT_REUSE_RING = 4u, EMIT_REUSE_ALWAYS = 8u;
 template <bool kStreaming>
 __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t *obs_chunk,
-                                           int8_t *mask_chunk, int nvalid, uint32_t skip = 0u) {
+                                           int8_t *mask_chunk, int nvalid, uint32_t opts = 0u) {
+    const uint32_t skip = opts & 3u;
     uint4 *img = reinterpret_cast<uint4 *>(stage);
     const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage + OBS_IMG_BYTES);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid == 32) {
         if (kBulkStore) {
-            if (lane == 0 && !(skip & 1u)) bulk_store_issue(obs_chunk, stage, OBS_IMG_BYTES);
+            if (lane == 0 && !(skip & 1u)) {
+                if (opts & EMIT_REUSE_ALWAYS) bulk_store_wait_all();
+                else if (opts & EMIT_REUSE_RING) bulk_store_wait_all_but_latest();
+                bulk_store_issue(obs_chunk, stage, OBS_IMG_BYTES);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

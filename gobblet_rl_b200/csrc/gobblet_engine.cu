@@ -8,6 +8,14 @@
 #include "../../include/gobblet_b200.h"
 #include "gobblet_core.cuh"
 
+// gobblet_host.c (plain C, gcc): thread pool + bit -> byte expansion of the packed wire format
+extern "C" {
+void gblh_job_begin(const uint32_t *rec, int64_t n, int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated,
+                    uint8_t *truncated, uint8_t *agent_id, int32_t nthreads);
+void gblh_job_publish(int64_t ready_envs);
+void gblh_job_finish(void);
+}
+
 namespace gbl {
 
 #ifndef GBL_BLOCK
@@ -16,11 +24,7 @@ namespace gbl {
 #ifndef GBL_STEP_MIN_BLOCKS
 #define GBL_STEP_MIN_BLOCKS (1024 / GBL_BLOCK)   // resident blocks per SM requested for step_kernel
 #endif
-#ifndef GBL_ROLLOUT_BLOCK
-#define GBL_ROLLOUT_BLOCK GBL_BLOCK   // threads per block of the fused rollout kernel (dynamic shared memory)
-#endif
 constexpr int BLOCK = GBL_BLOCK, WARPS = BLOCK / 32;
-constexpr int RBLOCK = GBL_ROLLOUT_BLOCK, RWARPS = RBLOCK / 32, RMIN_BLOCKS = 1024 / RBLOCK;
 
 // ---- block-level statistics reduction: shuffles -> shared -> one atomic per slot per block ----
 template <int NW = WARPS>
@@ -105,8 +109,10 @@ __global__ void __launch_bounds__(BLOCK, GBL_STEP_MIN_BLOCKS) step_kernel(StepPa
         uint32_t action = 255u;
         if (valid) {
             env_unpack(e, p.state[g]);
+            // out-of-range actions are ILLEGAL moves (AssertOutOfBoundsWrapper territory, gobblet.py:115), mapped to
+            // the sentinel 254; exactly 255 is reserved for "not stepped" under GBL_ACTION_SKIP_255
             long long a = (long long)static_cast<const ActT *>(p.actions)[g];
-            action = (a < 0 || a > 254) ? 255u : (uint32_t)a;
+            action = (a < 0 || a > 255) ? 254u : (uint32_t)a;
         }
         uint32_t u, up, m0, m1;
         occupancy(e, u, up);
@@ -115,7 +121,9 @@ __global__ void __launch_bounds__(BLOCK, GBL_STEP_MIN_BLOCKS) step_kernel(StepPa
         occupancy(e, u, up);
         legal_mask(e.xo, e.yo, u, up, m0, m1);
         const bool same_step = (p.flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_SAME_STEP;
-        if (same_step && !r.acted) r.term = false;     // skipped env: nothing to reset
+        // a skipped env is never reset; an env that ARRIVES finished (state imported from an "off" / "next_step"
+        // run) reports its flags once more and is reset by this call, like the oracle's gbo_env_step
+        const bool do_reset = same_step && r.term && !r.skipped;
         if (same_step) {
             if (p.final_obs && p.final_mask) {      // terminal observation before it is replaced
                 __syncwarp();
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(BLOCK, GBL_STEP_MIN_BLOCKS) step_kernel(StepPa
                 emit_chunk<kStreaming>(stage[warp], lane, p.final_obs + first * GBL_OBS_BYTES,
                                        p.final_mask + first * GBL_MASK_BYTES, nvalid);
             }
-            if (r.term) {
+            if (do_reset) {
                 env_clear(e);
                 occupancy(e, u, up);
                 legal_mask(e.xo, e.yo, u, up, m0, m1);
@@ -159,16 +167,21 @@ struct RolloutParams {
     int32_t ring;
     int8_t *rew_out;
     uint8_t *term_out, *agent_out, *action_log;
+    int8_t *final_obs_out, *final_mask_out;
     int64_t *stats;
     uint32_t flags;
 };
 
-// kAux: any of rew_out / term_out / agent_out / action_log is requested (compiled out otherwise)
-template <bool kFast, bool kStreaming, bool kAux>
-__global__ void __launch_bounds__(RBLOCK, RMIN_BLOCKS) rollout_kernel(RolloutParams p) {
-    extern __shared__ __align__(16) uint8_t stage_all[];      // RWARPS * STAGE_BYTES, one staging area per warp
+// kFast: same-step auto-reset, so every env is live at every step and every sampled action is legal (a valid
+//        position always has >= 10 legal actions: both large pieces of the mover can move and <= 4 squares carry
+//        a large top).  The one exception is an env that ARRIVES finished (state imported from an "off" /
+//        "next_step" run): its first step only resets it, exactly as the general path and the oracle do.
+// kAux:  any of rew_out / term_out / agent_out / action_log / final_*_out is requested (compiled out otherwise)
+template <bool kFast, bool kStreaming, bool kAux, int kBlock>
+__global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) uint8_t stage_all[];      // (kBlock/32) * STAGE_BYTES, one staging area per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * RBLOCK + threadIdx.x, first = g - lane;
+    const int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x, first = g - lane;
     uint8_t *const stage = stage_all + warp * STAGE_BYTES;
     const bool valid = g < p.n;
     Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -179,7 +192,8 @@ __global__ void __launch_bounds__(RBLOCK, RMIN_BLOCKS) rollout_kernel(RolloutPar
         Env e;
         env_clear(e);
         if (valid) env_unpack(e, p.state[g]);
-        const uint32_t plies_start = e.plies;
+        uint32_t plies_start = e.plies, live_steps = (uint32_t)p.T;
+        bool dead0 = kFast && e.done;
         uint32_t u, up, m0, m1;
         occupancy(e, u, up);
         legal_mask(e.xo, e.yo, u, up, m0, m1);
@@ -187,18 +201,36 @@ __global__ void __launch_bounds__(RBLOCK, RMIN_BLOCKS) rollout_kernel(RolloutPar
         __syncwarp();
         const uint64_t step_base = p.step_base_dev ? *p.step_base_dev : p.step_base;
         uint4 rnd = make_uint4(0, 0, 0, 0);
-        uint32_t slot = (uint32_t)(step_base % (uint64_t)p.ring);
+        uint32_t slot = (p.flags & GBL_SLOT_FROM_ZERO) ? 0u : (uint32_t)(step_base % (uint64_t)p.ring);
         const bool emit = p.obs_out != nullptr;
+        const uint32_t opts = ((p.flags >> 8) & 3u) |        // GBL_MEASURE_SKIP_*_STORES
+                              (p.ring >= p.T ? 0u : p.ring == 1 ? EMIT_REUSE_ALWAYS : EMIT_REUSE_RING);
 #pragma unroll 2
         for (int32_t t = 0; t < p.T; ++t) {     // two plies per trip: the own/opponent register swap becomes renaming
             const uint64_t s = step_base + (uint64_t)t;
             if (t == 0 || (s & 3u) == 0) rnd = draw_block(p.seed, p.env_id_base + (uint64_t)g, s, 0u);
             uint32_t action = 255u;
-            if (kFast || !e.done) action = sample_action(m0, m1, pick_word(rnd, (uint32_t)s & 3u));
-            StepResult r = env_step<kFast>(e, m0, m1, action, p.flags, st);
-            if (r.term && same_step) env_clear(e);
+            StepResult r;
+            if (kFast && dead0) {               // reset-only step of an env that arrived finished
+                r = {0, 0, true, e.trunc != 0, false, false};
+                dead0 = false; plies_start = 0; --live_steps;
+            } else {
+                if (kFast || !e.done) action = sample_action(m0, m1, pick_word(rnd, (uint32_t)s & 3u));
+                r = env_step<kFast>(e, m0, m1, action, p.flags, st);
+            }
             occupancy(e, u, up);
             legal_mask(e.xo, e.yo, u, up, m0, m1);
+            if (kAux && p.final_obs_out) {      // the observation a same-step reset is about to replace
+                stage_env(stage, cfg, lane, e, m0, m1);
+                __syncwarp();
+                emit_chunk<kStreaming>(stage, lane, p.final_obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
+                                       p.final_mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
+                __syncwarp();
+            }
+            if (r.term && same_step) {          // raw_env.reset: empty board, player_1 to move, every action legal
+                env_clear(e);
+                m0 = 0xFFFFFFFFu; m1 = 0x003FFFFFu;
+            }
             if (kAux && valid) {
                 const int64_t o = (int64_t)slot * p.n + g;
                 if (p.rew_out) *reinterpret_cast<char2 *>(p.rew_out + 2 * o) = make_char2((signed char)r.r1, (signed char)r.r2);
@@ -210,34 +242,65 @@ __global__ void __launch_bounds__(RBLOCK, RMIN_BLOCKS) rollout_kernel(RolloutPar
                 stage_env(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
                 emit_chunk<kStreaming>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
-                                       p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid,
-                                       (p.flags >> 8) & 3u);   // GBL_MEASURE_SKIP_*_STORES
+                                       p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
         }
         if (kBulkStore && lane == 0) bulk_store_wait_all();
         if (valid) p.state[g] = env_pack(e);
-        if (kFast) {   // every step was a live, legal step: these follow from the step count
-            st.steps = (uint32_t)p.T;
-            st.sumlen = plies_start + (uint32_t)p.T - e.plies;
+        if (kFast) {   // every step but a reset-only first one was a live, legal step: these follow from the step count
+            st.steps = live_steps;
+            st.sumlen = plies_start + live_steps - e.plies;
             st.p2w = st.episodes - st.p1w;
         }
     }
-    if (p.stats) flush_stats<RWARPS>(st, valid, p.stats);
+    if (p.stats) flush_stats<kBlock / 32>(st, valid, p.stats);
 }
 
 // ---- masked-uniform sampler over int8 masks -----------------------------------------------------
+// A warp owns 32 consecutive mask rows = 1728 contiguous bytes = 108 x 16 bytes: the lanes load them as
+// coalesced 128-bit vectors, squeeze every 16 bytes into 16 bits ("byte != 0") and park the 1728-bit stream in
+// shared memory; each lane then cuts its own 54 bits out of the stream.  (One thread per row reading 54 single
+// bytes at a 54-byte stride -- the first version -- touches every 32-byte sector 32 times.)
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w) {   // 4 bytes -> 4 bits, bit i = byte i != 0
+    const uint32_t t = (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;
+    return (((t >> 7) * 0x01020408u) >> 24) & 0xFu;
+}
+
 __global__ void __launch_bounds__(BLOCK)
 sample_legal_kernel(const int8_t *__restrict__ mask, uint64_t seed, uint64_t env_id_base, uint64_t step,
                     const uint64_t *step_dev, int32_t *act, int64_t n) {
-    int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (g >= n) return;
+    __shared__ uint32_t bits[WARPS][56];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x, first = g - lane;
+    if (first >= n) return;
     if (step_dev) step = *step_dev;
-    const int8_t *m = mask + g * GBL_MASK_BYTES;
+    const int8_t *rows = mask + first * GBL_MASK_BYTES;
     uint32_t m0 = 0, m1 = 0;
-    for (int a = 0; a < 32; ++a) m0 |= (uint32_t)(m[a] != 0) << a;
-    for (int a = 32; a < 54; ++a) m1 |= (uint32_t)(m[a] != 0) << (a - 32);
+    if (n - first >= 32 && (reinterpret_cast<uintptr_t>(rows) & 15u) == 0) {
+        uint16_t *hb = reinterpret_cast<uint16_t *>(bits[warp]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t q = lane + 32u * i;
+            if (i < 3 || q < MASK_VEC) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rows) + q);
+                hb[q] = (uint16_t)(nonzero_nibble(v.x) | (nonzero_nibble(v.y) << 4) | (nonzero_nibble(v.z) << 8) |
+                                   (nonzero_nibble(v.w) << 12));
+            }
+        }
+        if (lane < 2) bits[warp][54 + lane] = 0;
+        __syncwarp();
+        const uint32_t o = 54u * lane, w = o >> 5, sh = o & 31u;
+        const uint32_t a = bits[warp][w], b = bits[warp][w + 1], c = bits[warp][w + 2];
+        m0 = __funnelshift_r(a, b, sh);
+        m1 = __funnelshift_r(b, c, sh) & 0x003FFFFFu;
+    } else if (g < n) {     // ragged last warp / unaligned base: byte loads
+        const int8_t *m = mask + g * GBL_MASK_BYTES;
+        for (int a = 0; a < 32; ++a) m0 |= (uint32_t)(m[a] != 0) << a;
+        for (int a = 32; a < 54; ++a) m1 |= (uint32_t)(m[a] != 0) << (a - 32);
+    }
+    if (g >= n) return;
     uint4 b = draw_block(seed, env_id_base + (uint64_t)g, step, 0u);
     act[g] = (m0 | m1) ? (int32_t)sample_action(m0, m1, pick_word(b, (uint32_t)step & 3u)) : -1;
 }
@@ -262,19 +325,115 @@ export_squares_kernel(const ulonglong2 *__restrict__ state, int8_t *squares, uin
 }
 
 __global__ void __launch_bounds__(BLOCK)
-import_squares_kernel(ulonglong2 *state, const int8_t *__restrict__ squares, const uint8_t *__restrict__ agent, int64_t n) {
+import_squares_kernel(ulonglong2 *state, const int8_t *__restrict__ squares, const uint8_t *__restrict__ agent,
+                      int32_t *invalid_count, int64_t n) {
     int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (g >= n) return;
     uint32_t x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+    bool bad = false;
     for (int i = 0; i < 27; ++i) {
         int l = i / 9, val = squares[g * 27 + i];
         if (val == 2 * l + 1) x1 |= 1u << i;
         else if (val == 2 * l + 2) y1 |= 1u << i;
         else if (val == -(2 * l + 1)) x2 |= 1u << i;
         else if (val == -(2 * l + 2)) y2 |= 1u << i;
+        else if (val != 0) bad = true;               // a piece on a level that is not its size's, or |val| > 6
+    }
+    const uint32_t w[4] = {x1, y1, x2, y2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int f = 0; f < 3; ++f) bad |= __popc(w[k] & (0x1FFu << (9 * f))) > 1;   // a piece placed twice (board.py:94-95)
+    if (bad) {
+        x1 = y1 = x2 = y2 = 0;
+        if (invalid_count) atomicAdd(invalid_count, 1);
     }
     uint64_t meta = agent ? (uint64_t)(agent[g] & 1u) : 0ull;
     state[g] = make_ulonglong2((uint64_t)x1 | ((uint64_t)y1 << 27) | (meta << 54), (uint64_t)x2 | ((uint64_t)y2 << 27));
+}
+
+// ---- packed wire format (include/gobblet_b200.h): the step for host-side consumers ----------------------
+// observation BITMAP, bit pos*13+c (gobblet.py:188-208), from the mover-relative boards
+__device__ __forceinline__ void obs_bits(const Env &e, uint64_t &lo, uint64_t &hi) {
+    lo = hi = 0;
+    const uint32_t w[4] = {e.xo, e.yo, e.xp, e.yp};
+    const int plane0[4] = {0, 1, 6, 7};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const uint32_t fld = w[k] & (0x1FFu << (9 * f));              // one-hot or empty
+            const uint32_t bit = 13u * (bfind(fld) - 9u * f) + (uint32_t)(plane0[k] + 2 * f);
+            const uint64_t one = fld ? 1ull : 0ull;
+            lo |= (bit < 64u ? one : 0ull) << (bit & 63u);
+            hi |= (bit >= 64u ? one : 0ull) << (bit & 63u);
+        }
+    if (e.agent) {                                   // plane 12: bits 12 + 13 p  (gobblet.py:199-206)
+        lo |= 0x0008004002001000ull;                 // 12, 25, 38, 51
+        hi |= 0x0010008004002001ull;                 // 64, 77, 90, 103, 116
+    }
+}
+
+__device__ __forceinline__ void store_record(uint32_t *rec, int64_t g, const Env &e, uint32_t m0, uint32_t m1,
+                                             int r1, int r2, bool term, bool trunc) {
+    uint64_t lo, hi;
+    obs_bits(e, lo, hi);
+    const uint32_t fl = (uint32_t)(r1 + 1) | ((uint32_t)(r2 + 1) << 2) | ((uint32_t)term << 4) | ((uint32_t)trunc << 5) |
+                        (e.agent << 6);
+    uint2 *out = reinterpret_cast<uint2 *>(rec + 6 * g);               // 24-byte records: three 8-byte stores
+    out[0] = make_uint2((uint32_t)lo, (uint32_t)(lo >> 32));
+    out[1] = make_uint2((uint32_t)hi, (uint32_t)(hi >> 32) | (fl << 21));
+    out[2] = make_uint2(m0, m1);
+}
+
+struct PackedParams {
+    ulonglong2 *state;
+    const void *actions;
+    uint32_t *rec, *final_rec;
+    int64_t *stats;
+    int64_t n;
+    uint32_t flags;
+};
+
+template <typename ActT>
+__global__ void __launch_bounds__(BLOCK) step_packed_kernel(PackedParams p) {
+    const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = g < p.n;
+    Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+        Env e;
+        env_unpack(e, p.state[g]);
+        long long a = (long long)static_cast<const ActT *>(p.actions)[g];
+        const uint32_t action = (a < 0 || a > 255) ? 254u : (uint32_t)a;
+        uint32_t u, up, m0, m1;
+        occupancy(e, u, up);
+        legal_mask(e.xo, e.yo, u, up, m0, m1);
+        StepResult r = env_step<false>(e, m0, m1, action, p.flags, st);
+        occupancy(e, u, up);
+        legal_mask(e.xo, e.yo, u, up, m0, m1);
+        const bool same_step = (p.flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_SAME_STEP;
+        if (same_step) {
+            if (p.final_rec) store_record(p.final_rec, g, e, m0, m1, r.r1, r.r2, r.term, r.trunc);
+            if (r.term && !r.skipped) {
+                env_clear(e);
+                m0 = 0xFFFFFFFFu; m1 = 0x003FFFFFu;
+            }
+        }
+        store_record(p.rec, g, e, m0, m1, r.r1, r.r2, r.term, r.trunc);
+        p.state[g] = env_pack(e);
+    }
+    if (p.stats) flush_stats(st, valid, p.stats);
+}
+
+__global__ void __launch_bounds__(BLOCK) observe_packed_kernel(const ulonglong2 *__restrict__ state, uint32_t *rec, int64_t n) {
+    const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= n) return;
+    Env e;
+    env_unpack(e, state[g]);
+    uint32_t u, up, m0, m1;
+    occupancy(e, u, up);
+    legal_mask(e.xo, e.yo, u, up, m0, m1);
+    store_record(rec, g, e, m0, m1, 0, 0, e.done != 0, e.trunc != 0);
 }
 
 }  // namespace gbl
@@ -298,6 +457,38 @@ static int check_launch(const char *what) {
 }
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
+
+// threads per block of the fused rollout: 256 once the grid fills the machine, smaller blocks for small
+// batches so that >= 148 SMs (x 4 schedulers) get a warp each (BASELINE config 2, 4096 envs: latency-bound)
+static int rollout_block_for(int64_t n, uint32_t flags) {
+    const uint32_t hint = (flags >> GBL_BLOCK_HINT_SHIFT) & 7u;
+    if (hint) return hint == 1 ? 32 : hint == 2 ? 64 : hint == 3 ? 128 : 256;
+    const int64_t warps = (n + 31) / 32;
+    if (warps <= 2 * 148) return 32;       // at most ~2 warps per SM anyway: spread them
+    if (warps <= 8 * 148) return 64;
+    if (warps <= 32 * 148) return 128;
+    return 256;
+}
+
+template <bool F, bool S, bool A, int B>
+static void launch_rollout(const RolloutParams &p, cudaStream_t s) {
+    const unsigned grid = (unsigned)((p.n + B - 1) / B);
+    const size_t smem = (size_t)(B / 32) * STAGE_BYTES;
+    rollout_kernel<F, S, A, B><<<grid, B, smem, s>>>(p);
+}
+template <bool F, bool S, bool A>
+static void launch_rollout_b(const RolloutParams &p, int block, cudaStream_t s) {
+    if constexpr (!S) {
+        launch_rollout<F, S, A, 256>(p, s);                      // plain stores: measurement aid, one size
+    } else {
+        switch (block) {
+            case 32: return launch_rollout<F, S, A, 32>(p, s);
+            case 64: return launch_rollout<F, S, A, 64>(p, s);
+            case 128: return launch_rollout<F, S, A, 128>(p, s);
+            default: return launch_rollout<F, S, A, 256>(p, s);
+        }
+    }
+}
 
 extern "C" {
 
@@ -358,39 +549,37 @@ int gbl_step(void *state, const void *actions, int32_t action_bytes, int8_t *obs
 int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_t env_id_base, uint64_t step_base,
                        const uint64_t *step_base_dev, int8_t *obs_out, int8_t *mask_out, int64_t obs_slot_stride, int64_t mask_slot_stride,
                        int32_t ring, int8_t *rew_out, uint8_t *term_out, uint8_t *agent_out, uint8_t *action_log,
-                       int64_t *stats, uint32_t flags, void *stream) {
+                       int8_t *final_obs_out, int8_t *final_mask_out, int64_t *stats, uint32_t flags, void *stream) {
     if (n < 0 || T < 0) return fail(GBL_E_INVALID, "gbl_rollout_random: n or T < 0");
     if (n == 0 || T == 0) return 0;
     if (!state || !aligned16(state)) return fail(GBL_E_INVALID, "gbl_rollout_random: bad state pointer");
     if ((obs_out == nullptr) != (mask_out == nullptr)) return fail(GBL_E_INVALID, "gbl_rollout_random: obs_out and mask_out go together");
+    if ((final_obs_out == nullptr) != (final_mask_out == nullptr) || (final_obs_out && !obs_out))
+        return fail(GBL_E_INVALID, "gbl_rollout_random: final_obs_out and final_mask_out go together and need obs_out / mask_out");
     if (ring < 1) return fail(GBL_E_INVALID, "gbl_rollout_random: ring must be >= 1");
     if (obs_out) {
         if (!aligned16(obs_out) || !aligned16(mask_out) || (obs_slot_stride & 15) || (mask_slot_stride & 15))
             return fail(GBL_E_INVALID, "gbl_rollout_random: obs/mask bases and slot strides must be multiples of 16 bytes");
+        if (final_obs_out && (!aligned16(final_obs_out) || !aligned16(final_mask_out)))
+            return fail(GBL_E_INVALID, "gbl_rollout_random: final_obs_out / final_mask_out must be 16-byte aligned");
         if (ring > 1 && (obs_slot_stride < n * GBL_OBS_BYTES || mask_slot_stride < n * GBL_MASK_BYTES))
             return fail(GBL_E_INVALID, "gbl_rollout_random: slot stride smaller than one step of output");
     }
     if ((flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_MASK) return fail(GBL_E_INVALID, "gbl_rollout_random: bad autoreset mode");
     if (rew_out && (reinterpret_cast<uintptr_t>(rew_out) & 1u)) return fail(GBL_E_INVALID, "gbl_rollout_random: rew_out must be 2-byte aligned");
     RolloutParams p = {(ulonglong2 *)state, n, T, seed, env_id_base, step_base, step_base_dev, obs_out, mask_out,
-                       obs_slot_stride, mask_slot_stride, ring, rew_out, term_out, agent_out, action_log, stats, flags};
-    // random legal actions never hit the illegal path; with same-step auto-reset no env is ever dead
+                       obs_slot_stride, mask_slot_stride, ring, rew_out, term_out, agent_out, action_log,
+                       final_obs_out, final_mask_out, stats, flags};
+    // random legal actions never hit the illegal path; with same-step auto-reset no env stays dead
     const bool fast = (flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_SAME_STEP;
     const bool plain = flags & GBL_STORE_DEFAULT_POLICY;
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((n + RBLOCK - 1) / RBLOCK);
-    const size_t smem = (size_t)RWARPS * STAGE_BYTES;
-    const bool aux = rew_out || term_out || agent_out || action_log;
-#define GBL_LAUNCH_ROLLOUT_1(F, S, A)                                                                            \
-    do {                                                                                                         \
-        if (smem > 48 * 1024)                                                                                    \
-            cudaFuncSetAttribute(rollout_kernel<F, S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        rollout_kernel<F, S, A><<<grid, RBLOCK, smem, s>>>(p);                                                   \
-    } while (0)
+    const int block = rollout_block_for(n, flags);
+    const bool aux = rew_out || term_out || agent_out || action_log || final_obs_out;
 #define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
     do {                                                                            \
-        if (aux) GBL_LAUNCH_ROLLOUT_1(F, S, true);                                  \
-        else GBL_LAUNCH_ROLLOUT_1(F, S, false);                                     \
+        if (aux) launch_rollout_b<F, S, true>(p, block, s);                         \
+        else launch_rollout_b<F, S, false>(p, block, s);                            \
     } while (0)
     if (fast) {
         if (plain) GBL_LAUNCH_ROLLOUT(true, false);
@@ -400,7 +589,6 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
         else GBL_LAUNCH_ROLLOUT(false, true);
     }
 #undef GBL_LAUNCH_ROLLOUT
-#undef GBL_LAUNCH_ROLLOUT_1
     return check_launch("gbl_rollout_random");
 }
 
@@ -421,12 +609,110 @@ int gbl_export_squares(const void *state, int8_t *squares, uint8_t *agent, int64
     return check_launch("gbl_export_squares");
 }
 
-int gbl_import_squares(void *state, const int8_t *squares, const uint8_t *agent, int64_t n, void *stream) {
+int gbl_import_squares(void *state, const int8_t *squares, const uint8_t *agent, int64_t n, int32_t *invalid_count,
+                       void *stream) {
     if (n < 0) return fail(GBL_E_INVALID, "gbl_import_squares: n < 0");
     if (n == 0) return 0;
     if (!state || !squares || !aligned16(state)) return fail(GBL_E_INVALID, "gbl_import_squares: bad pointer");
-    import_squares_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>((ulonglong2 *)state, squares, agent, n);
+    import_squares_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>((ulonglong2 *)state, squares, agent, invalid_count, n);
     return check_launch("gbl_import_squares");
+}
+
+int gbl_step_packed(void *state, const void *actions, int32_t action_bytes, uint32_t *rec, uint32_t *final_rec,
+                    int64_t *stats, int64_t n, uint32_t flags, void *stream) {
+    if (n < 0) return fail(GBL_E_INVALID, "gbl_step_packed: n < 0");
+    if (n == 0) return 0;
+    if (!state || !actions || !rec || !aligned16(state) || (reinterpret_cast<uintptr_t>(rec) & 7u) ||
+        (reinterpret_cast<uintptr_t>(final_rec) & 7u))
+        return fail(GBL_E_INVALID, "gbl_step_packed: state/actions/rec must be non-null, state 16-byte and rec 8-byte aligned");
+    if ((flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_MASK) return fail(GBL_E_INVALID, "gbl_step_packed: bad autoreset mode");
+    PackedParams p = {(ulonglong2 *)state, actions, rec, final_rec, stats, n, flags};
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (action_bytes) {
+        case 1: step_packed_kernel<uint8_t><<<grid_for(n), BLOCK, 0, s>>>(p); break;
+        case 4: step_packed_kernel<int32_t><<<grid_for(n), BLOCK, 0, s>>>(p); break;
+        case 8: step_packed_kernel<int64_t><<<grid_for(n), BLOCK, 0, s>>>(p); break;
+        default: return fail(GBL_E_INVALID, "gbl_step_packed: action_bytes must be 1, 4 or 8");
+    }
+    return check_launch("gbl_step_packed");
+}
+
+int gbl_observe_packed(const void *state, uint32_t *rec, int64_t n, void *stream) {
+    if (n < 0) return fail(GBL_E_INVALID, "gbl_observe_packed: n < 0");
+    if (n == 0) return 0;
+    if (!state || !rec || !aligned16(state) || (reinterpret_cast<uintptr_t>(rec) & 7u))
+        return fail(GBL_E_INVALID, "gbl_observe_packed: bad pointer");
+    observe_packed_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>((const ulonglong2 *)state, rec, n);
+    return check_launch("gbl_observe_packed");
+}
+
+// ---- host side of the wire format: gobblet_host.c does the work, this file only knows CUDA events ------
+int gbl_host_unpack_chunked(const uint32_t *rec, int64_t n, int32_t nchunks, const int64_t *chunk_end, void *const *events,
+                            int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated, uint8_t *truncated,
+                            uint8_t *agent_id, int32_t nthreads) {
+    if (n < 0 || nchunks < 0 || (n > 0 && (!rec || !obs || !mask))) return fail(GBL_E_INVALID, "gbl_host_unpack_chunked: bad argument");
+    if (n == 0) return 0;
+    if (nchunks > 0 && (!chunk_end || chunk_end[nchunks - 1] != n)) return fail(GBL_E_INVALID, "gbl_host_unpack_chunked: chunk_end must end at n");
+    gblh_job_begin(rec, n, obs, mask, rew2, terminated, truncated, agent_id, nthreads);
+    int rc = 0;
+    for (int32_t c = 0; c < nchunks; ++c) {
+        if (events && events[c]) {
+            cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[c]);
+            if (e != cudaSuccess && rc == 0) {
+                snprintf(g_err, sizeof(g_err), "gbl_host_unpack_chunked: %s", cudaGetErrorString(e));
+                rc = GBL_E_CUDA;
+            }
+        }
+        gblh_job_publish(chunk_end[c]);
+    }
+    if (nchunks == 0) gblh_job_publish(n);
+    gblh_job_finish();
+    return rc;
+}
+
+int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t flags, uint8_t *d_actions, uint32_t *d_rec,
+                  uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *const *streams, void *const *events,
+                  int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id,
+                  int64_t *stats, int32_t nthreads) {
+    if (n < 0 || nchunks < 1) return fail(GBL_E_INVALID, "gbl_step_host: n < 0 or nchunks < 1");
+    if (n == 0) return 0;
+    if (!state || !actions_host || !d_actions || !d_rec || !h_rec || !chunk_end || !streams || !events || !aligned16(state) ||
+        (reinterpret_cast<uintptr_t>(d_rec) & 7u) || (obs == nullptr) != (mask == nullptr))
+        return fail(GBL_E_INVALID, "gbl_step_host: null / misaligned pointer, or obs and mask not given together");
+    if (chunk_end[nchunks - 1] != n) return fail(GBL_E_INVALID, "gbl_step_host: chunk_end must end at n");
+    if ((flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_MASK) return fail(GBL_E_INVALID, "gbl_step_host: bad autoreset mode");
+    // enqueue every chunk: actions H2D -> step (packed records) -> records D2H -> event
+    int64_t a = 0;
+    for (int32_t c = 0; c < nchunks; ++c) {
+        const int64_t b = chunk_end[c], m = b - a;
+        if (m < 0 || b > n || (a & 1)) return fail(GBL_E_INVALID, "gbl_step_host: chunk_end must ascend in even steps");
+        cudaStream_t s = (cudaStream_t)streams[c];
+        if (m > 0) {
+            cudaMemcpyAsync(d_actions + a, actions_host + a, (size_t)m, cudaMemcpyHostToDevice, s);
+            PackedParams p = {(ulonglong2 *)state + a, d_actions + a, d_rec + 6 * a, nullptr, stats, m, flags};
+            step_packed_kernel<uint8_t><<<grid_for(m), BLOCK, 0, s>>>(p);
+            cudaMemcpyAsync(h_rec + 6 * a, d_rec + 6 * a, (size_t)m * 24, cudaMemcpyDeviceToHost, s);
+        }
+        cudaEventRecord((cudaEvent_t)events[c], s);
+        a = b;
+    }
+    int rc = check_launch("gbl_step_host");
+    if (rc != 0 || !obs) {                       // packed consumer (or failure): just wait for the copies
+        for (int32_t c = 0; c < nchunks; ++c) {
+            cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[c]);
+            if (e != cudaSuccess && rc == 0) {
+                snprintf(g_err, sizeof(g_err), "gbl_step_host: %s", cudaGetErrorString(e));
+                rc = GBL_E_CUDA;
+            }
+        }
+        return rc;
+    }
+    return gbl_host_unpack_chunked(h_rec, n, nchunks, chunk_end, events, obs, mask, rew2, terminated, truncated, agent_id, nthreads);
+}
+
+int gbl_host_unpack(const uint32_t *rec, int64_t n, int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated,
+                    uint8_t *truncated, uint8_t *agent_id, int32_t nthreads) {
+    return gbl_host_unpack_chunked(rec, n, 0, nullptr, nullptr, obs, mask, rew2, terminated, truncated, agent_id, nthreads);
 }
 
 }  // extern "C"

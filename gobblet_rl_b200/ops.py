@@ -16,7 +16,10 @@ ILLEGAL_TERMINATE, ILLEGAL_PASS = 0x0, 0x1
 AUTORESET_OFF, AUTORESET_SAME_STEP, AUTORESET_NEXT_STEP = 0 << 1, 1 << 1, 2 << 1
 STORE_DEFAULT_POLICY = 0x8
 ACTION_SKIP_255 = 0x10
-ABI_VERSION = 2
+SLOT_FROM_ZERO = 0x20
+BLOCK_HINT_SHIFT = 12
+REC_WORDS = 6                      # packed wire format: 6 x u32 = 24 bytes per env (include/gobblet_b200.h)
+ABI_VERSION = 3
 
 _ILLEGAL = {"terminate": ILLEGAL_TERMINATE, "pass": ILLEGAL_PASS}
 _AUTORESET = {"off": AUTORESET_OFF, "same_step": AUTORESET_SAME_STEP, "next_step": AUTORESET_NEXT_STEP}
@@ -43,11 +46,20 @@ def _load():
         "gbl_reset_masked": (C.c_int, [vp, vp, i64, vp]),
         "gbl_observe": (C.c_int, [vp, vp, vp, vp, i64, vp]),
         "gbl_step": (C.c_int, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, u32, vp]),
-        "gbl_rollout_random": (C.c_int, [vp, i64, i32, u64, u64, u64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, u32, vp]),
+        "gbl_rollout_random": (C.c_int, [vp, i64, i32, u64, u64, u64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+        "gbl_step_packed": (C.c_int, [vp, vp, i32, vp, vp, vp, i64, u32, vp]),
+        "gbl_observe_packed": (C.c_int, [vp, vp, i64, vp]),
+        "gbl_host_unpack": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, i32]),
+        "gbl_host_unpack_chunked": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+        "gbl_step_host": (C.c_int, [vp, vp, i64, u32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+        "gbl_host_fill": (C.c_int, [vp, i64, i32, i32]),
+        "gbl_host_threads": (C.c_int, [i32]),
+        "gbl_host_simd": (C.c_int, []),
+        "gbl_host_set_store_mode": (C.c_int, [i32]),
         "gbl_sample_legal": (C.c_int, [vp, u64, u64, u64, vp, vp, i64, vp]),
         "gbl_greedy": (C.c_int, [vp, vp, vp, i32, u64, u64, vp, vp, vp, vp, i64, vp]),
         "gbl_export_squares": (C.c_int, [vp, vp, vp, i64, vp]),
-        "gbl_import_squares": (C.c_int, [vp, vp, vp, i64, vp]),
+        "gbl_import_squares": (C.c_int, [vp, vp, vp, i64, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
@@ -60,7 +72,9 @@ def _load():
 LIB, LIB_PATH = _load()
 EXPORTED_SYMBOLS = ("gbl_abi_version", "gbl_last_error", "gbl_reset", "gbl_reset_masked", "gbl_observe",
                     "gbl_step", "gbl_rollout_random", "gbl_sample_legal", "gbl_greedy", "gbl_export_squares",
-                    "gbl_import_squares")
+                    "gbl_import_squares", "gbl_step_packed", "gbl_observe_packed", "gbl_host_unpack",
+                    "gbl_host_unpack_chunked", "gbl_step_host", "gbl_host_fill", "gbl_host_threads", "gbl_host_simd",
+                    "gbl_host_set_store_mode")
 
 
 class GobbletError(RuntimeError):
@@ -152,14 +166,16 @@ def step(state: torch.Tensor, actions: torch.Tensor, obs: torch.Tensor, mask: to
 
 @torch.library.custom_op("gobblet_b200::rollout_random",
                          mutates_args=("state", "obs_out", "mask_out", "rew_out", "term_out", "agent_out",
-                                       "action_log", "stats"))
+                                       "action_log", "stats", "final_obs_out", "final_mask_out"))
 def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, step_base: int,
                    obs_out: Optional[torch.Tensor], mask_out: Optional[torch.Tensor],
                    rew_out: Optional[torch.Tensor], term_out: Optional[torch.Tensor],
                    agent_out: Optional[torch.Tensor], action_log: Optional[torch.Tensor],
-                   stats: Optional[torch.Tensor], flags: int, step_dev: Optional[torch.Tensor] = None) -> None:
+                   stats: Optional[torch.Tensor], flags: int, step_dev: Optional[torch.Tensor] = None,
+                   final_obs_out: Optional[torch.Tensor] = None, final_mask_out: Optional[torch.Tensor] = None) -> None:
     """obs_out [ring, n, 3, 3, 13] / mask_out [ring, n, 54] (possibly views of padded slots).
-    step_dev: optional int64[1] CUDA tensor holding the absolute step (replaces step_base; graph-capturable)."""
+    step_dev: optional int64[1] CUDA tensor holding the absolute step (replaces step_base; graph-capturable).
+    final_obs_out / final_mask_out: same shape and slot strides as obs_out / mask_out (terminal observations)."""
     dev = _need_cuda(state, rew_out, term_out, agent_out, action_log, stats, step_dev)
     n = state.shape[0]
     ring, so, sm = 1, 0, 0
@@ -184,10 +200,43 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
             raise GobbletError("per-step outputs must share one ring length (that of obs_out when it is given)")
     _need_bytes("rew_out", rew_out, ring * n * 2); _need_bytes("term_out", term_out, ring * n)
     _need_bytes("agent_out", agent_out, ring * n); _need_bytes("action_log", action_log, T * n)
+    if (final_obs_out is None) != (final_mask_out is None):
+        raise GobbletError("final_obs_out / final_mask_out go together")
+    if final_obs_out is not None:
+        if obs_out is None or not (final_obs_out.is_cuda and final_mask_out.is_cuda):
+            raise GobbletError("final_obs_out / final_mask_out need obs_out / mask_out and must be CUDA tensors")
+        if (final_obs_out.shape != obs_out.shape or final_mask_out.shape != mask_out.shape or final_obs_out.stride(0) != so
+                or final_mask_out.stride(0) != sm or final_obs_out.element_size() != 1 or final_mask_out.element_size() != 1
+                or not final_obs_out[0].is_contiguous() or not final_mask_out[0].is_contiguous()):
+            raise GobbletError("final_obs_out / final_mask_out must match obs_out / mask_out in shape and slot stride")
     with torch.cuda.device(dev):
         _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(step_dev), _ptr(obs_out),
                                       _ptr(mask_out), so, sm, ring, _ptr(rew_out), _ptr(term_out), _ptr(agent_out),
-                                      _ptr(action_log), _ptr(stats), flags, _stream(state)))
+                                      _ptr(action_log), _ptr(final_obs_out), _ptr(final_mask_out), _ptr(stats), flags,
+                                      _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::step_packed", mutates_args=("state", "rec", "final_rec", "stats"))
+def step_packed(state: torch.Tensor, actions: torch.Tensor, rec: torch.Tensor, final_rec: Optional[torch.Tensor],
+                stats: Optional[torch.Tensor], flags: int) -> None:
+    """gbl_step in the packed wire format: rec int32 [n, 6] (24 bytes per env, include/gobblet_b200.h)."""
+    dev = _need_cuda(state, actions, rec, final_rec, stats)
+    n = _need_state(state)
+    if actions.dtype not in (torch.uint8, torch.int32, torch.int64) or actions.numel() != n:
+        raise GobbletError("actions must be uint8 / int32 / int64 with one entry per env")
+    _need_bytes("rec", rec, 24 * n, 4); _need_bytes("final_rec", final_rec, 24 * n, 4); _need_bytes("stats", stats, 64, 8)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_step_packed(_ptr(state), _ptr(actions), actions.element_size(), _ptr(rec), _ptr(final_rec),
+                                   _ptr(stats), n, flags, _stream(state)))
+
+
+@torch.library.custom_op("gobblet_b200::observe_packed", mutates_args=("rec",))
+def observe_packed(state: torch.Tensor, rec: torch.Tensor) -> None:
+    dev = _need_cuda(state, rec)
+    n = _need_state(state)
+    _need_bytes("rec", rec, 24 * n, 4)
+    with torch.cuda.device(dev):
+        _check(LIB.gbl_observe_packed(_ptr(state), _ptr(rec), n, _stream(state)))
 
 
 @torch.library.custom_op("gobblet_b200::sample_legal", mutates_args=("act",))
@@ -224,14 +273,89 @@ def export_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[t
         _check(LIB.gbl_export_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::import_squares", mutates_args=("state",))
-def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor]) -> None:
-    dev = _need_cuda(state, squares, agent)
+@torch.library.custom_op("gobblet_b200::import_squares", mutates_args=("state", "invalid_count"))
+def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor],
+                   invalid_count: Optional[torch.Tensor] = None) -> None:
+    """invalid_count: optional int32[1] CUDA tensor, incremented per env whose squares the reference would reject
+    (a piece placed twice, board.py:94-95) or could never hold; such envs are loaded as the empty board."""
+    dev = _need_cuda(state, squares, agent, invalid_count)
     n = _need_state(state)
-    _need_bytes("squares", squares, 27 * n); _need_bytes("agent", agent, n)
+    _need_bytes("squares", squares, 27 * n); _need_bytes("agent", agent, n); _need_bytes("invalid_count", invalid_count, 4, 4)
     with torch.cuda.device(dev):
-        _check(LIB.gbl_import_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
+        _check(LIB.gbl_import_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _ptr(invalid_count),
+                                      _stream(state)))
 
 
-for _op in (reset, observe, step, rollout_random, sample_legal, greedy, export_squares, import_squares):
+for _op in (reset, observe, step, rollout_random, step_packed, observe_packed, sample_legal, greedy, export_squares,
+            import_squares):
     _op.register_fake(lambda *a, **k: None)
+
+
+# ---- host side of the packed wire format (plain host memory; no torch custom op: nothing here is traced) ----
+def host_unpack(rec, obs, mask, rew=None, terminated=None, truncated=None, agent_id=None, threads: int = 0,
+                chunk_end=None, events=None):
+    """Expand packed records (host tensor int32 [n, 6]) into reference-shaped HOST tensors obs int8 [n,3,3,13],
+    mask int8 [n,54], rew int8 [n,2], terminated / truncated / agent_id (1 byte each) on the library's thread
+    pool.  chunk_end (list of env counts) + events (torch.cuda.Event per chunk): envs of chunk c are expanded
+    once events[c] has completed, overlapping the expansion with the remaining D2H copies."""
+    n = rec.shape[0]
+    for name, t, per_env in (("rec", rec, 24), ("obs", obs, OBS_BYTES), ("mask", mask, MASK_BYTES), ("rew", rew, 2),
+                             ("terminated", terminated, 1), ("truncated", truncated, 1), ("agent_id", agent_id, 1)):
+        if t is None:
+            continue
+        if t.is_cuda or not t.is_contiguous():
+            raise GobbletError(f"host_unpack: {name} must be a contiguous HOST tensor")
+        if t.numel() * t.element_size() < n * per_env:
+            raise GobbletError(f"host_unpack: {name} too small")
+    if chunk_end is None:
+        rc = LIB.gbl_host_unpack(_ptr(rec), n, _ptr(obs), _ptr(mask), _ptr(rew), _ptr(terminated), _ptr(truncated),
+                                 _ptr(agent_id), threads)
+    else:
+        k = len(chunk_end)
+        ends = (C.c_int64 * k)(*[int(x) for x in chunk_end])
+        evs = (C.c_void_p * k)(*[None if e is None else e.cuda_event for e in (events or [None] * k)])
+        rc = LIB.gbl_host_unpack_chunked(_ptr(rec), n, k, ends, evs, _ptr(obs), _ptr(mask), _ptr(rew), _ptr(terminated),
+                                         _ptr(truncated), _ptr(agent_id), threads)
+    _check(rc)
+
+
+class HostStepPlan:
+    """Pre-marshalled arguments of gbl_step_host (chunk table, stream / event handles): the per-step cost on the
+    Python side is ONE ctypes call."""
+
+    def __init__(self, state, d_actions, d_rec, h_rec, chunk_end, streams, events, outputs, stats, flags, threads=0):
+        k = len(chunk_end)
+        self.keep = (state, d_actions, d_rec, h_rec, streams, events, outputs, stats)    # keep the buffers alive
+        self.n, self.k, self.flags, self.threads = state.shape[0], k, int(flags), int(threads)
+        self.ends = (C.c_int64 * k)(*[int(x) for x in chunk_end])
+        self.streams = (C.c_void_p * k)(*[s.cuda_stream for s in streams])
+        for e in events:
+            e.record(streams[0])                 # torch creates the cudaEvent lazily: make the handles exist
+        self.events = (C.c_void_p * k)(*[e.cuda_event for e in events])
+        self.ptrs = [_ptr(t) for t in (state, d_actions, d_rec, h_rec)]
+        self.out = [_ptr(t) for t in outputs] if outputs is not None else [None] * 6
+        self.stats = _ptr(stats)
+        self.device = state.device
+
+    def run(self, actions_host: torch.Tensor):
+        if actions_host.is_cuda or actions_host.dtype != torch.uint8 or actions_host.numel() != self.n:
+            raise GobbletError("actions must be a host uint8 tensor with one entry per env")
+        st, da, dr, hr = self.ptrs
+        with torch.cuda.device(self.device):
+            _check(LIB.gbl_step_host(st, _ptr(actions_host), self.n, self.flags, da, dr, hr, self.k, self.ends, self.streams,
+                                     self.events, *self.out, self.stats, self.threads))
+
+
+def host_fill(t: torch.Tensor, threads: int = 0, mode: int = 0):
+    """Measurement aid: fill a host tensor with the expander's thread pool (mode 0 = non-temporal stores)."""
+    if t.is_cuda or not t.is_contiguous():
+        raise GobbletError("host_fill needs a contiguous host tensor")
+    _check(LIB.gbl_host_fill(_ptr(t), t.numel() * t.element_size(), threads, mode))
+
+
+def host_threads(threads: int = 0) -> int:
+    return int(LIB.gbl_host_threads(threads))
+
+
+def host_simd() -> str:
+    return "avx512bw" if LIB.gbl_host_simd() else "table"

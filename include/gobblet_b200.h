@@ -43,7 +43,7 @@ extern "C" {
 #define GBL_API
 #endif
 
-#define GBL_ABI_VERSION 2
+#define GBL_ABI_VERSION 3
 #define GBL_OBS_BYTES 117
 #define GBL_MASK_BYTES 54
 #define GBL_STATE_BYTES 16
@@ -56,7 +56,11 @@ extern "C" {
 #define GBL_AUTORESET_SAME_STEP (1u << 1)
 #define GBL_AUTORESET_NEXT_STEP (2u << 1)
 #define GBL_AUTORESET_MASK (3u << 1)
-#define GBL_ACTION_SKIP_255 0x10u     /* gbl_step: action 255 leaves that env untouched (Tianshou steps a SUBSET of env ids) */
+#define GBL_ACTION_SKIP_255 0x10u     /* gbl_step: action EXACTLY 255 leaves that env untouched (Tianshou steps a SUBSET of env ids);
+                                         every other value outside [0,54) is an illegal move */
+#define GBL_SLOT_FROM_ZERO 0x20u      /* gbl_rollout_random: step t goes to ring slot t % ring (not (step_base+t) % ring):
+                                         the launch writes straight into the slots of a caller's trajectory buffer */
+#define GBL_BLOCK_HINT_SHIFT 12       /* gbl_rollout_random: bits 12-14 = threads per block, 0 auto, 1..4 = 32/64/128/256 (tuning aid) */
 #define GBL_MEASURE_SKIP_OBS_STORES 0x100u  /* gbl_rollout_random only: measurement aid, do everything but the obs stores */
 #define GBL_MEASURE_SKIP_MASK_STORES 0x200u /* gbl_rollout_random only: measurement aid, do everything but the mask stores */
 #define GBL_STORE_DEFAULT_POLICY 0x8u /* use plain st.global instead of streaming (evict-first) stores */
@@ -98,12 +102,68 @@ GBL_API int gbl_step(void *state, const void *actions, int32_t action_bytes, int
  * launch, so a CUDA graph holding this launch advances through the Philox stream when the caller bumps
  * the counter inside the same graph.
  * Nullable: obs_out+mask_out (simulate only), rew_out [ring][n][2], term_out [ring][n],
- * agent_out [ring][n], action_log [T][n] (255 = no action), stats. */
+ * agent_out [ring][n], action_log [T][n] (255 = no action), final_obs_out+final_mask_out (same ring and
+ * slot strides as obs_out / mask_out: the observation BEFORE a same-step reset replaces it = Tianshou's
+ * obs_next, collector_manual_policy.py:80-106), stats.
+ * An env that arrives finished under same-step auto-reset spends its first step being reset (no action,
+ * action_log 255, terminated reported once more), like gbl_step. */
 GBL_API int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_t env_id_base,
                        uint64_t step_base, const uint64_t *step_base_dev, int8_t *obs_out, int8_t *mask_out,
                        int64_t obs_slot_stride, int64_t mask_slot_stride, int32_t ring,
                        int8_t *rew_out, uint8_t *term_out, uint8_t *agent_out, uint8_t *action_log,
-                       int64_t *stats, uint32_t flags, void *stream);
+                       int8_t *final_obs_out, int8_t *final_mask_out, int64_t *stats, uint32_t flags, void *stream);
+
+/* ---- packed wire format: the same step for HOST-side consumers -------------------------------------------
+ * The observation planes and the mask are 171 bytes of 0/1 per env; across PCIe they travel as BITS.
+ * One record = 6 little-endian u32 (24 bytes) per env:
+ *   w0..w3  bit i (i = pos*13 + c, the byte index of gobblet.py:188-208) of the 128-bit value = obs byte i;
+ *           bits 117-118 = rewards[player_1] + 1, 119-120 = rewards[player_2] + 1, 121 = terminated,
+ *           122 = truncated, 123 = agent_selection, 124-127 = 0
+ *   w4, w5  bit a of the 64-bit value = action_mask[a], bits 54-63 = 0          (gobblet.py:209-213)
+ * gbl_step_packed = gbl_step writing `rec` [n][6] (and `final_rec`, nullable: the terminal observation under
+ * same-step auto-reset) instead of the expanded tensors: 24 instead of 176 bytes per env cross PCIe.
+ * gbl_observe_packed = gbl_observe in the same format (rewards 0, flags as the env carries them). */
+GBL_API int gbl_step_packed(void *state, const void *actions, int32_t action_bytes, uint32_t *rec, uint32_t *final_rec,
+                    int64_t *stats, int64_t n, uint32_t flags, void *stream);
+GBL_API int gbl_observe_packed(const void *state, uint32_t *rec, int64_t n, void *stream);
+
+/* HOST side of the wire format (all pointers are HOST pointers; runs on a persistent thread pool inside the
+ * library -- its only global state; calls are serialised by a mutex).  Expands n records into the
+ * reference-shaped arrays obs int8 [n][3][3][13], mask int8 [n][54] (gobblet.py:179-215), rew2 int8 [n][2],
+ * terminated / truncated / agent_id uint8 [n] (each nullable).  nthreads <= 0: one thread per core of the
+ * calling thread's affinity mask.  AVX-512BW (64 bits -> 64 bytes per instruction, non-temporal stores) when
+ * the CPU has it, a table-driven path otherwise; both produce identical bytes.
+ * gbl_host_unpack_chunked additionally takes `nchunks` cudaEvent_t handles: envs [chunk_end[c-1], chunk_end[c])
+ * are expanded as soon as events[c] has completed (the D2H copy of that chunk), so the expansion of one chunk
+ * overlaps the PCIe transfer of the next. */
+GBL_API int gbl_host_unpack(const uint32_t *rec, int64_t n, int8_t *obs, int8_t *mask, int8_t *rew2,
+                    uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id, int32_t nthreads);
+GBL_API int gbl_host_unpack_chunked(const uint32_t *rec, int64_t n, int32_t nchunks, const int64_t *chunk_end,
+                            void *const *events, int8_t *obs, int8_t *mask, int8_t *rew2,
+                            uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id, int32_t nthreads);
+/* The whole end-to-end step for a HOST-side driver of n envs in ONE call -- `env.step(a); env.last()` per env
+ * (gobblet.py:231-273, :179-215) with host actions in and host arrays out:
+ *   per chunk c (envs [chunk_end[c-1], chunk_end[c]), boundaries even; multiples of 1024 keep the expander on its
+ *   fast path) on streams[c]:  actions_host -> d_actions (H2D), gbl_step_packed into d_rec, d_rec -> h_rec (D2H),
+ *   events[c];  then gbl_host_unpack_chunked expands every chunk as soon as its event has completed.
+ * Host pointers: actions_host (uint8, pinned for asynchronous copies), h_rec [n][6] (pinned), obs / mask / rew2 /
+ * terminated / truncated / agent_id (any host memory; obs == mask == NULL: no expansion, the caller consumes h_rec).
+ * Device pointers: state, d_actions [n], d_rec [n][6], stats.  streams / events: nchunks cudaStream_t / cudaEvent_t
+ * handles owned by the caller; the state must not be in use by other streams.  Returns after all results are in
+ * host memory. */
+GBL_API int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t flags, uint8_t *d_actions,
+                  uint32_t *d_rec, uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *const *streams,
+                  void *const *events, int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated,
+                  uint8_t *truncated, uint8_t *agent_id, int64_t *stats, int32_t nthreads);
+
+/* measurement aids: fill `bytes` of host memory with the pool (the write bandwidth the expander is bound by),
+ * the pool size a call with `nthreads` would use, and the expander variant (1 = AVX-512BW, 0 = table).
+ * mode: 0 = non-temporal stores, 1 = regular stores. */
+GBL_API int gbl_host_fill(void *dst, int64_t bytes, int32_t nthreads, int32_t mode);
+GBL_API int gbl_host_threads(int32_t nthreads);
+GBL_API int gbl_host_simd(void);
+/* GBL_HOST_STORE_MODE: gbl_host_set_store_mode(0) = staged + non-temporal (default), 1 = direct regular stores */
+GBL_API int gbl_host_set_store_mode(int32_t mode);
 
 /* Uniform sample over each mask row with the same Philox stream as the rollout
  * (random_admissible_policy_rllib.py:23-30, example_basic.py:58-61).  act[i] = -1 for an empty row.
@@ -125,8 +185,11 @@ GBL_API int gbl_greedy(const int8_t *obs, const int8_t *mask, const int16_t *pre
 /* Debug / interchange views of the reference's own state array (board.py:33):
  * squares int8 [n][27] signed piece numbers, agent uint8 [n] (0 = player_1 to move). */
 GBL_API int gbl_export_squares(const void *state, int8_t *squares, uint8_t *agent, int64_t n, void *stream);
+/* gbl_import_squares validates what Board.is_legal would reject (board.py:94-95: a piece placed twice) or
+ * could never hold (a piece on a level that is not its size's): such an env is loaded as the EMPTY board
+ * and, when invalid_count (nullable, device int32) is given, counted there. */
 GBL_API int gbl_import_squares(void *state, const int8_t *squares, const uint8_t *agent, int64_t n,
-                       void *stream);
+                       int32_t *invalid_count, void *stream);
 
 #ifdef __cplusplus
 }

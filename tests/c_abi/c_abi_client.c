@@ -25,7 +25,7 @@ int main(int argc, char **argv) {
     if (gbl_abi_version() != GBL_ABI_VERSION) { fprintf(stderr, "ABI mismatch\n"); return 1; }
     if (gbl_observe(state, obs + 1, mask, 0, n, 0) != GBL_E_INVALID) { fprintf(stderr, "misaligned obs accepted\n"); return 1; }
     CK(gbl_reset(state, n, 0));
-    CK(gbl_rollout_random(state, n, T, seed, 0, 0, 0, obs, mask, 0, 0, 1, 0, 0, 0, 0, stats, GBL_AUTORESET_SAME_STEP, 0));
+    CK(gbl_rollout_random(state, n, T, seed, 0, 0, 0, obs, mask, 0, 0, 1, 0, 0, 0, 0, 0, 0, stats, GBL_AUTORESET_SAME_STEP, 0));
     CK(gbl_step(state, actions, 8, obs, mask, rew, term, trunc, agent, 0, 0, stats, n, GBL_AUTORESET_SAME_STEP, 0));
     CU(cudaDeviceSynchronize());
     int8_t *h_obs = (int8_t *)malloc(n * GBL_OBS_BYTES), *h_mask = (int8_t *)malloc(n * GBL_MASK_BYTES), *h_rew = (int8_t *)malloc(2 * n);
@@ -43,5 +43,25 @@ int main(int argc, char **argv) {
     printf("stats %lld %lld %lld %lld %lld %lld %lld %lld\n", (long long)h_stats[0], (long long)h_stats[1], (long long)h_stats[2],
            (long long)h_stats[3], (long long)h_stats[4], (long long)h_stats[5], (long long)h_stats[6], (long long)h_stats[7]);
     printf("sums %lld %lld %lld %lld\n", so, sm, sr, st);
+
+    /* one more step through HOST buffers in a single call (gbl_step_host: packed records over PCIe, expanded by
+     * the library's thread pool): pinned actions in, reference-shaped host arrays out */
+    uint8_t *ha, *da; uint32_t *hrec, *drec; int8_t *xo, *xm, *xr; uint8_t *xt, *xu, *xa;
+    CU(cudaMallocHost((void **)&ha, n)); CU(cudaMallocHost((void **)&hrec, 24 * n)); CU(cudaMalloc((void **)&da, n)); CU(cudaMalloc((void **)&drec, 24 * n));
+    CU(cudaMallocHost((void **)&xo, n * GBL_OBS_BYTES)); CU(cudaMallocHost((void **)&xm, n * GBL_MASK_BYTES)); CU(cudaMallocHost((void **)&xr, 2 * n));
+    CU(cudaMallocHost((void **)&xt, n)); CU(cudaMallocHost((void **)&xu, n)); CU(cudaMallocHost((void **)&xa, n));
+    for (int64_t i = 0; i < n; ++i) ha[i] = (uint8_t)(i % 54);
+    cudaStream_t streams[2]; cudaEvent_t events[2];
+    for (int c = 0; c < 2; ++c) { CU(cudaStreamCreate(&streams[c])); CU(cudaEventCreateWithFlags(&events[c], cudaEventDisableTiming)); }
+    int64_t ends[2] = {n / 2 / 2 * 2, n};
+    CK(gbl_step_host(state, ha, n, GBL_AUTORESET_SAME_STEP, da, drec, hrec, 2, ends, (void *const *)streams, (void *const *)events,
+                     xo, xm, xr, xt, xu, xa, stats, 3));
+    so = sm = sr = st = 0;
+    long long su = 0, sa = 0;
+    for (int64_t i = 0; i < n * GBL_OBS_BYTES; ++i) so += (long long)xo[i] * (i % 251 + 1);
+    for (int64_t i = 0; i < n * GBL_MASK_BYTES; ++i) sm += (long long)xm[i] * (i % 251 + 1);
+    for (int64_t i = 0; i < 2 * n; ++i) sr += (long long)xr[i] * (i % 251 + 1);
+    for (int64_t i = 0; i < n; ++i) { st += xt[i]; su += xu[i]; sa += xa[i]; }
+    printf("host %lld %lld %lld %lld %lld %lld\n", so, sm, sr, st, su, sa);
     return 0;
 }

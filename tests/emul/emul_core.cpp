@@ -36,11 +36,11 @@ void emul_rollout(unsigned long long *state, int64_t n, int32_t T, uint64_t seed
     const bool fast = same_step;
     for (int64_t first = 0; first < n; first += 32) {
         int nvalid = (int)std::min<int64_t>(32, n - first);
-        Env e[32]; uint32_t m0[32], m1[32], plies_start[32]; uint4 rnd[32]; Stats st[32];
+        Env e[32]; uint32_t m0[32], m1[32], plies_start[32], live_steps[32]; uint4 rnd[32]; Stats st[32]; bool dead0[32];
         for (int l = 0; l < 32; ++l) {
             env_clear(e[l]); memset(&st[l], 0, sizeof(Stats));
             if (l < nvalid) env_unpack(e[l], {state[2 * (first + l)], state[2 * (first + l) + 1]});
-            plies_start[l] = e[l].plies;
+            plies_start[l] = e[l].plies; live_steps[l] = (uint32_t)T; dead0[l] = fast && e[l].done;
             uint32_t u, up; occupancy(e[l], u, up); legal_mask(e[l].xo, e[l].yo, u, up, m0[l], m1[l]);
         }
         for (int32_t t = 0; t < T; ++t) {
@@ -49,11 +49,17 @@ void emul_rollout(unsigned long long *state, int64_t n, int32_t T, uint64_t seed
                 int64_t g = first + l;
                 if (t == 0 || (s & 3) == 0) rnd[l] = draw_block(seed, env_id_base + g, s, 0);
                 uint32_t action = 255;
-                if (fast || !e[l].done) action = sample_action(m0[l], m1[l], pick_word(rnd[l], s & 3));
-                StepResult r = fast ? env_step<true>(e[l], m0[l], m1[l], action, flags, st[l])
-                                    : env_step<false>(e[l], m0[l], m1[l], action, flags, st[l]);
-                if (r.term && same_step) env_clear(e[l]);
+                StepResult r;
+                if (fast && dead0[l]) {
+                    r = {0, 0, true, e[l].trunc != 0, false, false};
+                    dead0[l] = false; plies_start[l] = 0; --live_steps[l];
+                } else {
+                    if (fast || !e[l].done) action = sample_action(m0[l], m1[l], pick_word(rnd[l], s & 3));
+                    r = fast ? env_step<true>(e[l], m0[l], m1[l], action, flags, st[l])
+                             : env_step<false>(e[l], m0[l], m1[l], action, flags, st[l]);
+                }
                 uint32_t u, up; occupancy(e[l], u, up); legal_mask(e[l].xo, e[l].yo, u, up, m0[l], m1[l]);
+                if (r.term && same_step) { env_clear(e[l]); m0[l] = 0xFFFFFFFFu; m1[l] = 0x003FFFFFu; }
                 if (l < nvalid) {
                     int64_t o = (int64_t)t * n + g;
                     rew[2 * o] = r.r1; rew[2 * o + 1] = r.r2; term[o] = r.term; agent[o] = e[l].agent;
@@ -66,8 +72,8 @@ void emul_rollout(unsigned long long *state, int64_t n, int32_t T, uint64_t seed
             ulonglong2 v = env_pack(e[l]);
             state[2 * (first + l)] = v.x; state[2 * (first + l) + 1] = v.y;
             if (fast) {
-                st[l].steps = (uint32_t)T;
-                st[l].sumlen = plies_start[l] + (uint32_t)T - e[l].plies;
+                st[l].steps = live_steps[l];
+                st[l].sumlen = plies_start[l] + live_steps[l] - e[l].plies;
                 st[l].p2w = st[l].episodes - st[l].p1w;
             }
             uint32_t a[8] = {st[l].episodes, st[l].p1w, st[l].p2w, st[l].steps, st[l].sumlen, st[l].illegal, st[l].both, st[l].maxlen};
@@ -91,7 +97,7 @@ void emul_step(unsigned long long *state, int64_t n, const int64_t *actions, uin
             if (l < nvalid) {
                 env_unpack(e[l], {state[2 * (first + l)], state[2 * (first + l) + 1]});
                 long long a = actions[first + l];
-                action = (a < 0 || a > 254) ? 255u : (uint32_t)a;
+                action = (a < 0 || a > 255) ? 254u : (uint32_t)a;
             }
             uint32_t u, up; occupancy(e[l], u, up); legal_mask(e[l].xo, e[l].yo, u, up, m0[l], m1[l]);
             r[l] = env_step<false>(e[l], m0[l], m1[l], action, flags, st[l]);
@@ -100,7 +106,7 @@ void emul_step(unsigned long long *state, int64_t n, const int64_t *actions, uin
         if (same_step) {
             if (fobs) warp_emit(e, m0, m1, fobs + first * 117, fmask + first * 54, nvalid);
             for (int l = 0; l < 32; ++l)
-                if (r[l].term) {
+                if (r[l].term && !r[l].skipped) {
                     env_clear(e[l]);
                     uint32_t u, up; occupancy(e[l], u, up); legal_mask(e[l].xo, e[l].yo, u, up, m0[l], m1[l]);
                 }

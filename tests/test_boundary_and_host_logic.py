@@ -18,11 +18,11 @@ def test_library_exports_every_declared_symbol():
     from gobblet_rl_b200 import ops
     header = open(os.path.join(REPO, "include", "gobblet_b200.h")).read()
     declared = sorted(set(re.findall(r"GBL_API\s+(?:const\s+)?\w+\s*\*?\s*(gbl_\w+)\s*\(", header)))
-    assert len(declared) == 11 and set(declared) == set(ops.EXPORTED_SYMBOLS)
+    assert len(declared) == 20 and set(declared) == set(ops.EXPORTED_SYMBOLS)
     lib = C.CDLL(ops.LIB_PATH)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.gbl_abi_version() == 2
+    assert lib.gbl_abi_version() == 3
     # the shipped SASS is sm_100a only, built from hand-written kernels (no PTX JIT, no other arch)
     out = subprocess.run(["cuobjdump", "-lelf", ops.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
@@ -38,6 +38,63 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(ops.GobbletError):
         ops.observe(torch.zeros((4, 2), dtype=torch.int64), torch.zeros((4, 3, 3, 13), dtype=torch.int8),
                     torch.zeros((4, 54), dtype=torch.int8), None)              # CPU tensors: no fallback
+
+
+def _random_records(n, rng):
+    rec = rng.integers(0, 2**32, (n, 6), dtype=np.uint64).astype(np.uint32)
+    rec[:, 3] &= np.uint32(0x0FFFFFFF)                       # spare bits 124-127 are zero on the wire
+    f = (rec[:, 3] >> 21) & 0xF
+    bad = ((f & 3) == 3) | (((f >> 2) & 3) == 3)             # rewards are -1 / 0 / +1 => fields 0 / 1 / 2
+    rec[bad, 3] &= np.uint32(~(0xF << 21) & 0xFFFFFFFF)
+    rec[:, 5] &= np.uint32((1 << 22) - 1)                    # mask bits 54-63 are zero
+    return rec
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 1024, 70001])
+def test_host_unpack_matches_the_wire_format_definition(n):
+    """gbl_host_unpack (thread pool; AVX-512 staged / direct stores, whatever the thread count) == the numpy
+    statement of the record layout in include/gobblet_b200.h (`vec_env.unpack_records`).  Host only: no GPU."""
+    from gobblet_rl_b200 import ops
+    from gobblet_rl_b200.vec_env import unpack_records
+    rec = _random_records(n, np.random.default_rng(n))
+    want = unpack_records(rec)
+    t = torch.from_numpy(rec.view(np.int32))
+    for mode in (0, 1):
+        assert ops.LIB.gbl_host_set_store_mode(mode) == 0
+        for threads in (1, 3, 0):
+            obs = torch.full((n, 3, 3, 13), 7, dtype=torch.int8); mask = torch.full((n, 54), 7, dtype=torch.int8)
+            rew = torch.full((n, 2), 7, dtype=torch.int8)
+            term, trunc, agent = (torch.full((n,), 7, dtype=torch.uint8) for _ in range(3))
+            ops.host_unpack(t, obs, mask, rew, term, trunc, agent, threads=threads)
+            got = (obs, mask, rew, term.bool(), trunc.bool(), agent)
+            for g, w in zip(got, want):
+                assert np.array_equal(g.numpy(), w), (n, mode, threads)
+            # chunked form without events (chunks are ready immediately) and with optional outputs left out
+            obs.fill_(7); mask.fill_(7)
+            ends = sorted({min(n, max(2, n // 3 // 2 * 2)), n})
+            ops.host_unpack(t, obs, mask, threads=threads, chunk_end=ends)
+            assert np.array_equal(obs.numpy(), want[0]) and np.array_equal(mask.numpy(), want[1])
+    ops.LIB.gbl_host_set_store_mode(0)
+
+
+def test_host_unpack_table_path_in_a_fresh_process(tmp_path):
+    """The portable (no AVX-512) expander is selected at first use: force it with GBL_HOST_SIMD=0 in a child."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np, torch\n"
+            "from gobblet_rl_b200 import ops\n"
+            "from gobblet_rl_b200.vec_env import unpack_records\n"
+            "assert ops.host_simd() == 'table'\n"
+            "rec = np.random.default_rng(1).integers(0, 2**32, (5000, 6), dtype=np.uint64).astype(np.uint32)\n"
+            "rec[:, 3] &= np.uint32(0x001FFFFF | (5 << 21) | (7 << 25)); rec[:, 5] &= np.uint32((1 << 22) - 1)\n"
+            "obs = torch.zeros((5000, 3, 3, 13), dtype=torch.int8); mask = torch.zeros((5000, 54), dtype=torch.int8)\n"
+            "rew = torch.zeros((5000, 2), dtype=torch.int8); f = [torch.zeros(5000, dtype=torch.uint8) for _ in range(3)]\n"
+            "ops.host_unpack(torch.from_numpy(rec.view(np.int32)), obs, mask, rew, *f, threads=2)\n"
+            "w = unpack_records(rec)\n"
+            "assert all(np.array_equal(g.numpy().astype(x.dtype), x) for g, x in zip((obs, mask, rew, *f), w))\n"
+            "print('OK')\n") % REPO
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GBL_HOST_SIMD="0"))
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
 
 
 def test_product_never_imports_the_oracle():

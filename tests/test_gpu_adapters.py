@@ -187,12 +187,15 @@ def test_captured_collection_graph_matches_eager(ad):
     assert torch.equal(va.state, vb.state) and va.stats.tolist() == vb.stats.tolist() and va.stats[5] == 0
 
 
-def test_host_vec_env_matches_oracle(ad):
+@pytest.mark.parametrize("wire,n,chunks", [("packed", 1003, 5), ("packed", 9000, 4), ("dense", 1003, 5), ("dense", 9000, 3)])
+def test_host_vec_env_matches_oracle(ad, wire, n, chunks):
     """The host-buffer path bench.py reports as `e2e`: pinned actions in, pinned obs / mask / rew / flags out,
-    chunked over CUDA streams -- same results as the oracle, whatever the chunking."""
+    chunked over CUDA streams -- same results as the oracle, whatever the chunking and whatever crosses PCIe
+    (24-byte packed records expanded by the host thread pool, or the expanded tensors themselves)."""
     from gobblet_rl_b200 import gobblet_v1
-    n, T = 1003, 25
-    host = gobblet_v1.HostVecEnv(n, chunks=5, seed=0, autoreset="same_step")
+    T = 25
+    host = gobblet_v1.HostVecEnv(n, chunks=chunks, wire=wire, seed=0, autoreset="same_step")
+    assert len(host.parts) == (1 if n < 2048 else chunks) and host.parts[-1][1] == n
     o = O.VecOracle(n, "terminate", "same_step")
     obs, mask, agent = host.reset()
     wobs, wmask, wagent = o.reset()
@@ -208,4 +211,50 @@ def test_host_vec_env_matches_oracle(ad):
         for g, ww in zip(got, w):
             assert np.array_equal(g.numpy(), ww), t
         wmask = w[1]
-    assert host.h2d_bytes_per_step == n and host.d2h_bytes_per_step == n * 176
+    assert host.h2d_bytes_per_step == n and host.host_bytes_per_step == n * 176
+    assert host.d2h_bytes_per_step == n * (24 if wire == "packed" else 176)
+    assert host.env.stats.tolist() == o.stats.tolist()
+
+
+def test_host_vec_env_packed_consumer(ad):
+    """expand=False: the consumer keeps the wire format; the records expand (numpy) to the oracle's arrays."""
+    from gobblet_rl_b200 import gobblet_v1
+    from gobblet_rl_b200.vec_env import unpack_records
+    n = 4096
+    host = gobblet_v1.HostVecEnv(n, chunks=2, expand=False, seed=0)
+    o = O.VecOracle(n)
+    _, wmask, _ = o.reset()
+    host.reset()
+    acts = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for t in range(6):
+        a = np.array([np.flatnonzero(m)[t % m.sum()] for m in wmask], np.int64)
+        acts.copy_(torch.as_tensor(a, dtype=torch.uint8))
+        rec = host.step(acts)
+        assert rec.shape == (n, 6) and rec.is_pinned()
+        w = o.step(a)
+        for g, ww in zip(unpack_records(rec), w):
+            assert np.array_equal(g, ww), t
+        wmask = w[1]
+
+
+def test_fused_collection_equals_step_by_step_collection(ad):
+    """The built-in masked-uniform policy collects in ONE launch (fused rollout writing into the buffer slots,
+    terminal observations included); it must fill the buffer exactly like sample_legal + step per step."""
+    from gobblet_rl_b200 import gobblet_v1
+    n, T = 3000, 12
+    bufs = []
+    for fused in (True, False):
+        vec = gobblet_v1.vec_env(n, seed=5, env_id_base=40)
+        buf = ad.TrajectoryBuffer(T, n)
+        col = ad.VecCollector(vec, ad.RandomLegalPolicy(seed=21, env_id_base=40), buf, fused=fused)
+        assert col.fused == fused
+        launches = vec.kernel_launches
+        for _ in range(2):
+            col.collect(); col.roll()
+        assert vec.kernel_launches - launches == (2 if fused else 2 * T)
+        bufs.append((vec, buf, col))
+    (va, a, _), (vb, b, _) = bufs
+    for name in ("obs", "mask", "agent_id", "act", "rew", "terminated", "truncated", "final_obs", "final_mask"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(va.state, vb.state) and va.stats.tolist() == vb.stats.tolist() and a.terminated.any()
+    assert va.step_count == vb.step_count == 2 * T

@@ -28,3 +28,6 @@ def test_plain_c_client_matches_oracle(tmp_path):
     w = lambda a: int((a.reshape(-1).astype(np.int64) * (np.arange(a.size) % 251 + 1)).sum())  # noqa: E731
     assert [int(x) for x in lines["stats"].split()] == v.stats.tolist()
     assert [int(x) for x in lines["sums"].split()] == [w(obs), w(mask), w(rew), int(term.sum())]
+    # gbl_step_host: the same step through host buffers (packed wire format + host expander), actions i % 54
+    obs, mask, rew, term, trunc, agent = v.step(np.arange(n, dtype=np.int64) % 54)
+    assert [int(x) for x in lines["host"].split()] == [w(obs), w(mask), w(rew), int(term.sum()), int(trunc.sum()), int(agent.sum())]

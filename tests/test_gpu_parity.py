@@ -382,3 +382,223 @@ def test_synthetic_positions_observe_step_and_greedy(gv1):
     for i in range(6):
         assert np.array_equal(_np(g[i]), w[i]), i
     assert np.array_equal(_np(v.squares()[0]), o.squares())
+
+
+# ---- round 2: states the fast rollout path did not produce itself, the timed template instance, wire format ----
+def test_fast_rollout_from_a_checkpoint_with_finished_envs(gv1):
+    """An autoreset="off" run leaves finished envs in the state tensor; loaded into a same-step env the fused
+    (kFast) rollout must treat them as the general path and the oracle do: the first step only resets them."""
+    n, T = 2000, 30
+    src = gv1.vec_env(n, seed=4, autoreset="off")
+    src.rollout_random(12, emit=False)
+    assert 0 < int((src.state[:, 0] >> 55 & 1).sum()) < n                 # done bit of the packed state
+    o = O.VecOracle(n, "terminate", "off")
+    o.rollout_random(12, seed=4, per_step=False)
+    v = gv1.vec_env(n, seed=77)
+    v.load_state_dict({**src.state_dict(), "seed": 77})
+    assert v.step_count == 12
+    got = v.rollout_random(T, ring=T, per_step=True, log_actions=True)
+    o.flags = O.flags("terminate", "same_step")
+    stats_before = o.stats.copy()
+    want = o.rollout_random(T, seed=77, step_base=12)
+    order = [(12 + t) % T for t in range(T)]
+    assert (want["actions"][0] == 255).any()                     # reset-only first steps exist
+    assert np.array_equal(_np(got["actions"]), want["actions"])
+    for k in ("obs", "mask", "rew", "terminated", "agent_id"):
+        assert np.array_equal(_np(got[k])[order], want[k]), k
+    assert v.stats.tolist() == o.stats.tolist() and (o.stats != stats_before).any()
+    assert np.array_equal(_np(v.squares()[0]), o.squares())
+    # the per-step kernel agrees on the same imported state (an env that arrives finished is reset, not stuck)
+    s = gv1.vec_env(n, seed=77)
+    s.load_state_dict({**src.state_dict(), "seed": 77})
+    o2 = O.VecOracle(n, "terminate", "off")
+    o2.rollout_random(12, seed=4, per_step=False)
+    o2.flags = O.flags("terminate", "same_step")
+    acts = np.where(want["actions"][0] == 255, 0, want["actions"][0]).astype(np.int64)
+    g = s.step(torch.as_tensor(acts).cuda())
+    w = o2.step(acts)
+    for i in range(6):
+        assert np.array_equal(_np(g[i]), w[i]), i
+
+
+def test_rollout_from_finished_positions_set_by_squares(gv1):
+    """set_squares of positions that already hold a complete line, then the fused rollout (kFast)."""
+    n, T = 1500, 16
+    o = O.VecOracle(n, "terminate", "off")
+    o.rollout_random(14, seed=8, per_step=False)
+    sq, agent = o.squares(), o.observe()[2]
+    assert any(O.check_for_winner(s) != 0 for s in sq[:200])
+    v = gv1.vec_env(n, seed=3)
+    v.set_squares(sq, agent)
+    w = O.VecOracle(n, "terminate", "same_step")
+    w.set(sq, agent)
+    got = v.rollout_random(T, ring=T, per_step=True, log_actions=True)
+    want = w.rollout_random(T, seed=3)
+    for k in ("actions", "obs", "mask", "rew", "terminated", "agent_id"):
+        assert np.array_equal(_np(got[k]), want[k]), k
+    assert v.stats.tolist() == w.stats.tolist()
+
+
+def test_timed_template_instance_equals_the_checked_one_at_full_size(gv1):
+    """bench.py times rollout_kernel<fast, streaming, no-aux>; the oracle comparisons run the aux instance.
+    Device-side equality of both instances at BASELINE config 3 size: 2^20 envs x 64 steps, every observation and
+    mask byte of the trajectory, the state and the statistics."""
+    n, T = 1 << 20, 64
+    a = gv1.vec_env(n, seed=0)
+    b = gv1.vec_env(n, seed=0)
+    plain = a.rollout_random(T, ring=T)                                        # <true, true, false>
+    aux = b.rollout_random(T, ring=T, per_step=True, log_actions=True)         # <true, true, true>
+    for t in range(T):
+        assert torch.equal(plain["obs"][t], aux["obs"][t]) and torch.equal(plain["mask"][t], aux["mask"][t]), t
+    assert torch.equal(a.state, b.state) and torch.equal(a.stats, b.stats)
+    # and the aux instance is the oracle's on a slice small enough to replay on the CPU
+    k = 4096
+    o = O.VecOracle(k)
+    want = o.rollout_random(T, seed=0)
+    assert np.array_equal(_np(aux["actions"][:, :k]), want["actions"])
+    assert np.array_equal(_np(plain["obs"][:, :k]), want["obs"]) and np.array_equal(_np(plain["mask"][:, :k]), want["mask"])
+
+
+@pytest.mark.parametrize("n", [100, 4096, 40000])
+def test_rollout_block_sizes_and_short_rings_agree(gv1, n):
+    """Every block size of the fused rollout (32/64/128/256 threads, chosen from N by default) and every ring
+    length (slots rewritten within the launch: bulk stores ordered by wait_group) gives the same bytes."""
+    T = 24
+    ref = gv1.vec_env(n, seed=6)
+    base = ref.rollout_random(T, ring=T, per_step=True, log_actions=True, final=True)
+    for hint, ring in ((32, T), (64, T), (128, 2), (256, 1), (0, 3), (32, 1)):
+        v = gv1.vec_env(n, seed=6)
+        out = v.rollout_random(T, ring=ring, per_step=True, log_actions=True, final=True, block_hint=hint)
+        assert torch.equal(out["actions"], base["actions"]) and torch.equal(v.state, ref.state) and torch.equal(v.stats, ref.stats)
+        for s in range(max(0, T - ring), T):
+            for key in ("obs", "mask", "final_obs", "final_mask", "rew", "terminated", "agent_id"):
+                assert torch.equal(out[key][s % ring], base[key][s]), (hint, ring, s, key)
+
+
+def test_skip255_only_skips_exactly_255(gv1):
+    """GBL_ACTION_SKIP_255 reserves exactly 255; -1, 254, 256, 300 are illegal moves (AssertOutOfBoundsWrapper /
+    TerminateIllegalWrapper territory, gobblet.py:110-117), never silent no-ops."""
+    n = 64
+    v = gv1.vec_env(n, autoreset="off", skip255=True)
+    o = O.VecOracle(n, "terminate", "off", skip255=True)
+    acts = np.zeros(n, np.int64)
+    acts[0:8] = [-1, 300, 254, 256, 255, 54, -(2**40), 2**40]
+    g = v.step(torch.as_tensor(acts).cuda())
+    w = o.step(acts)
+    for i in range(6):
+        assert np.array_equal(_np(g[i]), w[i]), i
+    term = _np(g[3])
+    assert term[[0, 1, 2, 3, 5, 6, 7]].all() and not term[4]           # 255 alone was skipped
+    assert _np(g[2])[0].tolist() == [-1, 0] and int(v.stats[5]) == 7 and v.stats.tolist() == o.stats.tolist()
+    # uint8 actions: 255 skips, 254 is illegal
+    v2 = gv1.vec_env(4, autoreset="off", skip255=True)
+    g2 = v2.step(torch.tensor([255, 254, 0, 53], dtype=torch.uint8).cuda())
+    assert _np(g2[3]).tolist() == [False, True, False, False]
+
+
+def test_graph_safe_checkpoint_and_resume(gv1):
+    """graph_safe=True keeps the Philox step counter on the device; a checkpoint taken after CUDA-graph replays
+    (which advance only the device counter) must resume on the same random stream."""
+    n, T = 400, 4
+    v = gv1.vec_env(n, seed=9, graph_safe=True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        v.rollout_random(T, emit=False)
+        with torch.cuda.graph(g, stream=side):
+            v.rollout_random(T, emit=False)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    ckpt = v.state_dict()
+    assert ckpt["step_count"] == 4 * T == v.sampler_step()      # 1 eager launch + 3 replays (a capture runs nothing)
+    cont = v.rollout_random(9, ring=1, log_actions=True)["actions"].clone()
+    for graph_safe in (True, False):
+        w = gv1.vec_env(n, seed=1, graph_safe=graph_safe)
+        w.load_state_dict(ckpt)
+        again = w.rollout_random(9, ring=1, log_actions=True)["actions"]
+        assert torch.equal(cont, again) and torch.equal(w.state, v.state)
+    o = O.VecOracle(n)
+    want = o.rollout_random(4 * T + 9, seed=9)
+    assert np.array_equal(_np(cont), want["actions"][4 * T:])
+    # externally driven steps keep both counters in lockstep
+    v.step(torch.zeros(n, dtype=torch.int64, device="cuda"))
+    assert int(v.step_dev) == v.step_count == 4 * T + 10
+
+
+@pytest.mark.parametrize("illegal_mode", ["terminate", "pass"])
+@pytest.mark.parametrize("autoreset", ["same_step", "off", "next_step"])
+def test_packed_wire_format_step_bit_exact(gv1, illegal_mode, autoreset):
+    """gbl_step_packed / gbl_observe_packed: the 24-byte records expand (numpy statement of the layout AND the
+    library's host expander) to exactly what the oracle's step returns, terminal observation included."""
+    from gobblet_rl_b200 import ops
+    from gobblet_rl_b200.vec_env import unpack_records
+    n, T = 777, 40
+    rng = np.random.default_rng(5)
+    v = gv1.vec_env(n, illegal_mode=illegal_mode, autoreset=autoreset)
+    o = O.VecOracle(n, illegal_mode, autoreset)
+    wobs, mask, wagent = o.reset()
+    r0 = unpack_records(v.observe_packed().cpu())
+    assert np.array_equal(r0[0], wobs) and np.array_equal(r0[1], mask) and np.array_equal(r0[5], wagent) and not r0[2].any()
+    frec = torch.zeros((n, 6), dtype=torch.int32, device="cuda")
+    host = [torch.zeros((n, 3, 3, 13), dtype=torch.int8), torch.zeros((n, 54), dtype=torch.int8), torch.zeros((n, 2), dtype=torch.int8),
+            torch.zeros(n, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)]
+    for t in range(T):
+        acts = np.array([rng.choice(np.flatnonzero(m)) for m in mask], np.int64)
+        bad = rng.random(n) < 0.1
+        acts[bad] = rng.integers(-3, 60, bad.sum())
+        rec = v.step_packed(torch.as_tensor(acts).cuda(), final_rec=frec).cpu()
+        w = o.step(acts, want_final=True)
+        got = unpack_records(rec)
+        for i in range(6):
+            assert np.array_equal(got[i], w[i]), (t, i)
+        ops.host_unpack(rec, *host, threads=3)
+        for i in range(6):
+            assert np.array_equal(host[i].numpy().astype(w[i].dtype), w[i]), (t, i)
+        if autoreset == "same_step":
+            f = unpack_records(frec.cpu())
+            assert np.array_equal(f[0], w[6]) and np.array_equal(f[1], w[7])
+        assert (rec[:, 3].numpy().view(np.uint32) >> 28 == 0).all() and (rec[:, 5].numpy().view(np.uint32) >> 22 == 0).all()
+        mask = w[1]
+    assert v.stats.tolist() == o.stats.tolist() and v.stats[5] > 0
+
+
+def test_import_squares_rejects_what_the_reference_rejects(gv1):
+    """Board.is_legal raises when a piece sits on two squares (board.py:94-95); a piece on a level that is not
+    its size's cannot exist at all.  Both are refused; valid positions import unchanged."""
+    v = gv1.vec_env(4, autoreset="off")
+    sq = np.zeros((4, 27), np.int8)
+    sq[0, 0] = 1; sq[0, 4] = 1                 # piece 1 twice
+    sq[1, 3] = 5                               # a large piece on the small level
+    sq[2, 20] = -6; sq[2, 2] = 2               # fine
+    with pytest.raises(ValueError, match="2 position"):
+        v.set_squares(sq, np.zeros(4, np.uint8))
+    back = _np(v.squares()[0])
+    assert not back[0].any() and not back[1].any() and np.array_equal(back[2], sq[2])
+    v.set_squares(sq[[2, 2, 3, 3]], np.zeros(4, np.uint8))
+
+
+def test_sample_legal_coalesced_and_fallback_paths(gv1):
+    """Full warps take the 128-bit load + shared bit-stream path, the ragged last warp and a misaligned base the
+    byte path; int8, uint8 and bool masks; all equal the oracle's pick."""
+    from gobblet_rl_b200 import ops
+    rng = np.random.default_rng(3)
+    n = 32 * 40 + 13
+    mask = (rng.random((n, 54)) < 0.5).astype(np.int8)
+    mask[5] = 0
+    mask[70] = 1
+    mask[100] *= 77                                             # any non-zero byte counts as legal
+    want = [O.pick(m, O.draw(7, 1000 + i, 11)) if m.any() else -1 for i, m in enumerate(mask)]
+    dev = torch.as_tensor(mask).cuda()
+    for m in (dev, dev.view(torch.uint8), dev != 0):
+        act = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ops.sample_legal(m.contiguous(), 7, 1000, 11, act)
+        assert _np(act).tolist() == want
+    pad = torch.zeros(n * 54 + 64, dtype=torch.int8, device="cuda")
+    off = pad[2:2 + n * 54].view(n, 54)
+    off.copy_(dev)
+    act = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ops.sample_legal(off, 7, 1000, 11, act)
+    assert _np(act).tolist() == want
