@@ -16,7 +16,7 @@ vec = gobblet_v1.vec_env(n, seed=0)
 obs, mask = vec._ring_buffers(T)
 for name, extra, nbytes in (("both", 0, 171), ("obs only", 2 << 8, 117), ("mask only", 1 << 8, 54), ("none", 3 << 8, 0)):
     def run():
-        ops.rollout_random(vec.state, T, 0, 0, 0, obs, mask, None, None, None, None, vec.stats, vec.flags | extra)
+        ops.rollout_random(vec.state, T, 0, 0, 0, obs, mask, None, None, None, None, None, None, vec.stats, vec.flags | extra)
     for _ in range(3): run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -17,7 +17,7 @@ for pad_envs in (0, 16, 272, 1040, 4112, 16400, 65552, 262160):
     obs = torch.zeros((T, pad, 3, 3, 13), dtype=torch.int8, device="cuda")[:, :n]
     mask = torch.zeros((T, pad, 54), dtype=torch.int8, device="cuda")[:, :n]
     def run():
-        ops.rollout_random(vec.state, T, 0, 0, 0, obs, mask, None, None, None, None, vec.stats, vec.flags)
+        ops.rollout_random(vec.state, T, 0, 0, 0, obs, mask, None, None, None, None, None, None, vec.stats, vec.flags)
     for _ in range(3): run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -155,8 +155,8 @@ class VecCollector:
     def _collect_fused(self):
         b, v, p = self.buf, self.vec, self.policy
         ops.rollout_random(v.state, b.horizon, p.seed, p.env_id_base, p.step, b.obs[1:], b.mask[1:], b.rew,
-                           b.terminated.view(torch.uint8), b.agent_id[1:], b.act, v.stats, v.flags | ops.SLOT_FROM_ZERO,
-                           p.step_dev, b.final_obs, b.final_mask)
+                           b.terminated.view(torch.uint8), b.agent_id[1:], b.act, b.final_obs, b.final_mask, v.stats,
+                           v.flags | ops.SLOT_FROM_ZERO, p.step_dev)
         v._advance(b.horizon)
         p.advance(b.horizon)
         return b

@@ -671,43 +671,48 @@ int gbl_host_unpack_chunked(const uint32_t *rec, int64_t n, int32_t nchunks, con
 }
 
 int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t flags, uint8_t *d_actions, uint32_t *d_rec,
-                  uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *const *streams, void *const *events,
+                  uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *stream, void *const *events,
                   int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id,
                   int64_t *stats, int32_t nthreads) {
     if (n < 0 || nchunks < 1) return fail(GBL_E_INVALID, "gbl_step_host: n < 0 or nchunks < 1");
     if (n == 0) return 0;
-    if (!state || !actions_host || !d_actions || !d_rec || !h_rec || !chunk_end || !streams || !events || !aligned16(state) ||
+    if (!state || !actions_host || !d_actions || !d_rec || !h_rec || !chunk_end || !events || !aligned16(state) ||
         (reinterpret_cast<uintptr_t>(d_rec) & 7u) || (obs == nullptr) != (mask == nullptr))
         return fail(GBL_E_INVALID, "gbl_step_host: null / misaligned pointer, or obs and mask not given together");
     if (chunk_end[nchunks - 1] != n) return fail(GBL_E_INVALID, "gbl_step_host: chunk_end must end at n");
+    for (int32_t c = 0; c < nchunks; ++c)
+        if (chunk_end[c] < (c ? chunk_end[c - 1] : 0)) return fail(GBL_E_INVALID, "gbl_step_host: chunk_end must ascend");
     if ((flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_MASK) return fail(GBL_E_INVALID, "gbl_step_host: bad autoreset mode");
-    // enqueue every chunk: actions H2D -> step (packed records) -> records D2H -> event
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool expand = obs != nullptr;
+    if (expand) gblh_job_begin(h_rec, n, obs, mask, rew2, terminated, truncated, agent_id, nthreads);   // workers spin on `ready`
+    // one stream: actions H2D -> ONE step launch (packed records) -> the records D2H chunk by chunk, an event behind
+    // each chunk.  While the later copies are still being enqueued, chunks that have already landed are published
+    // to the expander (cudaEventQuery), so the host cores start on chunk 0 a few microseconds after it arrives.
+    cudaMemcpyAsync(d_actions, actions_host, (size_t)n, cudaMemcpyHostToDevice, s);
+    PackedParams p = {(ulonglong2 *)state, d_actions, d_rec, nullptr, stats, n, flags};
+    step_packed_kernel<uint8_t><<<grid_for(n), BLOCK, 0, s>>>(p);
+    int rc = check_launch("gbl_step_host");
+    int32_t published = 0;
     int64_t a = 0;
-    for (int32_t c = 0; c < nchunks; ++c) {
-        const int64_t b = chunk_end[c], m = b - a;
-        if (m < 0 || b > n || (a & 1)) return fail(GBL_E_INVALID, "gbl_step_host: chunk_end must ascend in even steps");
-        cudaStream_t s = (cudaStream_t)streams[c];
-        if (m > 0) {
-            cudaMemcpyAsync(d_actions + a, actions_host + a, (size_t)m, cudaMemcpyHostToDevice, s);
-            PackedParams p = {(ulonglong2 *)state + a, d_actions + a, d_rec + 6 * a, nullptr, stats, m, flags};
-            step_packed_kernel<uint8_t><<<grid_for(m), BLOCK, 0, s>>>(p);
-            cudaMemcpyAsync(h_rec + 6 * a, d_rec + 6 * a, (size_t)m * 24, cudaMemcpyDeviceToHost, s);
-        }
+    for (int32_t c = 0; c < nchunks && rc == 0; ++c) {
+        const int64_t b = chunk_end[c];
+        if (b > a) cudaMemcpyAsync(h_rec + 6 * a, d_rec + 6 * a, (size_t)(b - a) * 24, cudaMemcpyDeviceToHost, s);
         cudaEventRecord((cudaEvent_t)events[c], s);
         a = b;
+        while (expand && published < c && cudaEventQuery((cudaEvent_t)events[published]) == cudaSuccess)
+            gblh_job_publish(chunk_end[published++]);
     }
-    int rc = check_launch("gbl_step_host");
-    if (rc != 0 || !obs) {                       // packed consumer (or failure): just wait for the copies
-        for (int32_t c = 0; c < nchunks; ++c) {
-            cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[c]);
-            if (e != cudaSuccess && rc == 0) {
-                snprintf(g_err, sizeof(g_err), "gbl_step_host: %s", cudaGetErrorString(e));
-                rc = GBL_E_CUDA;
-            }
+    for (; published < nchunks; ++published) {       // wait for the rest in order
+        cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[published]);
+        if (e != cudaSuccess && rc == 0) {
+            snprintf(g_err, sizeof(g_err), "gbl_step_host: %s", cudaGetErrorString(e));
+            rc = GBL_E_CUDA;
         }
-        return rc;
+        if (expand) gblh_job_publish(chunk_end[published]);
     }
-    return gbl_host_unpack_chunked(h_rec, n, nchunks, chunk_end, events, obs, mask, rew2, terminated, truncated, agent_id, nthreads);
+    if (expand) gblh_job_finish();
+    return rc;
 }
 
 int gbl_host_unpack(const uint32_t *rec, int64_t n, int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated,

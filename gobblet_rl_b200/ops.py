@@ -171,8 +171,8 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
                    obs_out: Optional[torch.Tensor], mask_out: Optional[torch.Tensor],
                    rew_out: Optional[torch.Tensor], term_out: Optional[torch.Tensor],
                    agent_out: Optional[torch.Tensor], action_log: Optional[torch.Tensor],
-                   stats: Optional[torch.Tensor], flags: int, step_dev: Optional[torch.Tensor] = None,
-                   final_obs_out: Optional[torch.Tensor] = None, final_mask_out: Optional[torch.Tensor] = None) -> None:
+                   final_obs_out: Optional[torch.Tensor], final_mask_out: Optional[torch.Tensor],
+                   stats: Optional[torch.Tensor], flags: int, step_dev: Optional[torch.Tensor] = None) -> None:
     """obs_out [ring, n, 3, 3, 13] / mask_out [ring, n, 54] (possibly views of padded slots).
     step_dev: optional int64[1] CUDA tensor holding the absolute step (replaces step_base; graph-capturable).
     final_obs_out / final_mask_out: same shape and slot strides as obs_out / mask_out (terminal observations)."""
@@ -275,7 +275,7 @@ def export_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[t
 
 @torch.library.custom_op("gobblet_b200::import_squares", mutates_args=("state", "invalid_count"))
 def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor],
-                   invalid_count: Optional[torch.Tensor] = None) -> None:
+                   invalid_count: Optional[torch.Tensor]) -> None:
     """invalid_count: optional int32[1] CUDA tensor, incremented per env whose squares the reference would reject
     (a piece placed twice, board.py:94-95) or could never hold; such envs are loaded as the empty board."""
     dev = _need_cuda(state, squares, agent, invalid_count)
@@ -323,14 +323,14 @@ class HostStepPlan:
     """Pre-marshalled arguments of gbl_step_host (chunk table, stream / event handles): the per-step cost on the
     Python side is ONE ctypes call."""
 
-    def __init__(self, state, d_actions, d_rec, h_rec, chunk_end, streams, events, outputs, stats, flags, threads=0):
+    def __init__(self, state, d_actions, d_rec, h_rec, chunk_end, stream, events, outputs, stats, flags, threads=0):
         k = len(chunk_end)
-        self.keep = (state, d_actions, d_rec, h_rec, streams, events, outputs, stats)    # keep the buffers alive
+        self.keep = (state, d_actions, d_rec, h_rec, stream, events, outputs, stats)     # keep the buffers alive
         self.n, self.k, self.flags, self.threads = state.shape[0], k, int(flags), int(threads)
         self.ends = (C.c_int64 * k)(*[int(x) for x in chunk_end])
-        self.streams = (C.c_void_p * k)(*[s.cuda_stream for s in streams])
+        self.stream = stream.cuda_stream
         for e in events:
-            e.record(streams[0])                 # torch creates the cudaEvent lazily: make the handles exist
+            e.record(stream)                     # torch creates the cudaEvent lazily: make the handles exist
         self.events = (C.c_void_p * k)(*[e.cuda_event for e in events])
         self.ptrs = [_ptr(t) for t in (state, d_actions, d_rec, h_rec)]
         self.out = [_ptr(t) for t in outputs] if outputs is not None else [None] * 6
@@ -342,7 +342,7 @@ class HostStepPlan:
             raise GobbletError("actions must be a host uint8 tensor with one entry per env")
         st, da, dr, hr = self.ptrs
         with torch.cuda.device(self.device):
-            _check(LIB.gbl_step_host(st, _ptr(actions_host), self.n, self.flags, da, dr, hr, self.k, self.ends, self.streams,
+            _check(LIB.gbl_step_host(st, _ptr(actions_host), self.n, self.flags, da, dr, hr, self.k, self.ends, self.stream,
                                      self.events, *self.out, self.stats, self.threads))
 
 

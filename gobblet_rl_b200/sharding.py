@@ -47,6 +47,26 @@ def bind_to_gpu_numa_node(device_index: int) -> bool:
         return False
 
 
+def partition_host_cores(rank: int, world_size: int):
+    """Give every rank its own slice of the host cores.  After `bind_to_gpu_numa_node` a rank's affinity mask is its
+    GPU's NUMA-local core set, which the ranks of that node SHARE; the host-side expander of the packed wire format
+    (`HostVecEnv`) runs one thread per core of the mask, so ranks with the same mask split it into contiguous blocks
+    (8 GPUs on a 32-core box: 4 cores per rank).  Returns the cores this process is now confined to."""
+    mine = sorted(os.sched_getaffinity(0))
+    if world_size == 1 or not (dist.is_available() and dist.is_initialized()):
+        return mine
+    masks = [None] * world_size
+    dist.all_gather_object(masks, mine)
+    same = [r for r in range(world_size) if masks[r] == mine]
+    k, m = same.index(rank), len(same)
+    if len(mine) < m:
+        return mine                                  # fewer cores than ranks: nothing sensible to split
+    per = len(mine) // m
+    cores = mine[k * per:(k + 1) * per] if k < m - 1 else mine[k * per:]
+    os.sched_setaffinity(0, cores)
+    return cores
+
+
 def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """Whole-job statistics from per-rank int64[8] vectors -- the run's single collective: ONE all-gather of
     64 bytes per rank (slots 0-6 are summed, slot 7 is a maximum, so a plain SUM all-reduce would not do)."""

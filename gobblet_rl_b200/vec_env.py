@@ -143,7 +143,7 @@ class VecEnv:
 
     def _launch_rollout(self, T, obs_out, mask_out, rew_out, term_out, agent_out, log, fobs, fmask, flags):
         ops.rollout_random(self.state, int(T), self.seed, self.env_id_base, self.step_count, obs_out, mask_out,
-                           rew_out, term_out, agent_out, log, self.stats, flags, self.step_dev, fobs, fmask)
+                           rew_out, term_out, agent_out, log, fobs, fmask, self.stats, flags, self.step_dev)
         self._advance(T)
 
     def _ring_buffers(self, ring, attr="_rings"):
@@ -286,7 +286,7 @@ class HostVecEnv:
             outs = (self.h_obs, self.h_mask, self.h_rew, self.h_term.view(torch.uint8), self.h_trunc.view(torch.uint8),
                     self.h_agent) if self.expand else None
             self.plan = ops.HostStepPlan(self.env.state, self.d_actions, self.d_rec, self.h_rec, [b for _, b in self.parts],
-                                         self.streams, self.events, outs, self.env.stats, self.env.flags, self.host_threads)
+                                         self.streams[0], self.events, outs, self.env.stats, self.env.flags, self.host_threads)
         else:
             self.d2h_bytes_per_step = self.host_bytes_per_step
         torch.cuda.synchronize(self.device)
@@ -306,9 +306,9 @@ class HostVecEnv:
         agent_id) -- or the pinned records int32 [N,6] when expand=False; everything has landed on return."""
         e = self.env
         if self.wire == "packed":
-            self.plan.run(actions_host)            # ONE C-ABI call: gbl_step_host (copies, kernels, expansion)
+            self.plan.run(actions_host)            # ONE C-ABI call: gbl_step_host (copies, kernel, expansion)
             e.step_count += 1
-            e.kernel_launches += len(self.parts)
+            e.kernel_launches += 1
             return self._outputs() if self.expand else self.h_rec
         cur = torch.cuda.current_stream(self.device)
         u8 = lambda t: t.view(torch.uint8)  # noqa: E731

@@ -142,17 +142,18 @@ GBL_API int gbl_host_unpack_chunked(const uint32_t *rec, int64_t n, int32_t nchu
                             void *const *events, int8_t *obs, int8_t *mask, int8_t *rew2,
                             uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id, int32_t nthreads);
 /* The whole end-to-end step for a HOST-side driver of n envs in ONE call -- `env.step(a); env.last()` per env
- * (gobblet.py:231-273, :179-215) with host actions in and host arrays out:
- *   per chunk c (envs [chunk_end[c-1], chunk_end[c]), boundaries even; multiples of 1024 keep the expander on its
- *   fast path) on streams[c]:  actions_host -> d_actions (H2D), gbl_step_packed into d_rec, d_rec -> h_rec (D2H),
- *   events[c];  then gbl_host_unpack_chunked expands every chunk as soon as its event has completed.
- * Host pointers: actions_host (uint8, pinned for asynchronous copies), h_rec [n][6] (pinned), obs / mask / rew2 /
+ * (gobblet.py:231-273, :179-215) with host actions in and host arrays out.  On `stream`: actions_host -> d_actions
+ * (H2D), one gbl_step_packed launch into d_rec, then d_rec -> h_rec (D2H) in nchunks pieces (envs
+ * [chunk_end[c-1], chunk_end[c]); multiples of 1024 keep the expander on its fast path) with events[c] behind
+ * each piece; the host thread pool expands every piece as soon as its event has completed, so the expansion
+ * overlaps the remaining PCIe traffic.
+ * Host pointers: actions_host (uint8, pinned for an asynchronous copy), h_rec [n][6] (pinned), obs / mask / rew2 /
  * terminated / truncated / agent_id (any host memory; obs == mask == NULL: no expansion, the caller consumes h_rec).
- * Device pointers: state, d_actions [n], d_rec [n][6], stats.  streams / events: nchunks cudaStream_t / cudaEvent_t
- * handles owned by the caller; the state must not be in use by other streams.  Returns after all results are in
- * host memory. */
+ * Device pointers: state, d_actions [n], d_rec [n][6], stats.  stream / events: a cudaStream_t and nchunks
+ * cudaEvent_t handles owned by the caller; the state must not be in use by other streams.  Returns after all
+ * results are in host memory. */
 GBL_API int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t flags, uint8_t *d_actions,
-                  uint32_t *d_rec, uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *const *streams,
+                  uint32_t *d_rec, uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *stream,
                   void *const *events, int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated,
                   uint8_t *truncated, uint8_t *agent_id, int64_t *stats, int32_t nthreads);
 

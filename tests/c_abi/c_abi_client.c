@@ -54,7 +54,7 @@ int main(int argc, char **argv) {
     cudaStream_t streams[2]; cudaEvent_t events[2];
     for (int c = 0; c < 2; ++c) { CU(cudaStreamCreate(&streams[c])); CU(cudaEventCreateWithFlags(&events[c], cudaEventDisableTiming)); }
     int64_t ends[2] = {n / 2 / 2 * 2, n};
-    CK(gbl_step_host(state, ha, n, GBL_AUTORESET_SAME_STEP, da, drec, hrec, 2, ends, (void *const *)streams, (void *const *)events,
+    CK(gbl_step_host(state, ha, n, GBL_AUTORESET_SAME_STEP, da, drec, hrec, 2, ends, (void *)streams[0], (void *const *)events,
                      xo, xm, xr, xt, xu, xa, stats, 3));
     so = sm = sr = st = 0;
     long long su = 0, sa = 0;

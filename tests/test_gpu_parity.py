@@ -210,7 +210,7 @@ def test_abi_rejects_bad_arguments(gv1):
     with pytest.raises(ops.GobbletError):
         ops.greedy(v.obs, v.mask[:20], None, 2, 0, 0, torch.zeros(40, dtype=torch.int32, device="cuda"), None, None, None)
     with pytest.raises(ops.GobbletError):
-        ops.rollout_random(v.state.view(-1), 1, 0, 0, 0, None, None, None, None, None, None, None, v.flags)   # state shape
+        ops.rollout_random(v.state.view(-1), 1, 0, 0, 0, None, None, None, None, None, None, None, None, None, v.flags)   # state shape
 
 
 def test_million_env_properties(gv1):
@@ -293,7 +293,7 @@ def test_empty_and_degenerate_sizes(gv1):
     assert lib.gbl_greedy(None, None, None, 2, 0, 0, None, None, None, None, 0, None) == 0
     v = gv1.vec_env(77, seed=2)
     before = v.state.clone()
-    ops.rollout_random(v.state, 0, 2, 0, 0, None, None, None, None, None, None, v.stats, v.flags)
+    ops.rollout_random(v.state, 0, 2, 0, 0, None, None, None, None, None, None, None, None, v.stats, v.flags)
     assert torch.equal(v.state, before)
     out = v.rollout_random(10, ring=3)
     o = O.VecOracle(77)
