@@ -1,47 +1,130 @@
-"""BaseWrapper + the three wrappers of gobblet.py:110-117 (+ CaptureStdoutWrapper name)."""
-from .env import AECEnv
+"""The wrapper stack of gobblet.py:110-117 as ONE generic forwarding layer configured by a rule table.
 
-_MIRRORED = ("agent_selection", "rewards", "terminations", "truncations", "infos", "agents",
-             "_cumulative_rewards")
+PettingZoo 1.22.3 ships a class per wrapper; this stand-in (TEST INFRASTRUCTURE ONLY) models
+them as data: a layer forwards every call to the env below it and mirrors the AEC bookkeeping back, and each
+named wrapper is a row of RULES saying which guards run before `step` / `observe` / ... and which attributes are
+hidden before `reset`.  Deliberately unlike gobblet_rl_b200/_aec.py in construction, so the two are independent
+statements of the same published behaviour.
+"""
+from .env import AECEnv, TRANSITIONS, finished
+
+MIRRORED = ("agent_selection", "rewards", "terminations", "truncations", "infos", "agents", "_cumulative_rewards")
+STATIC = ("possible_agents", "metadata", "observation_spaces", "action_spaces")
 
 
-class BaseWrapper(AECEnv):
-    def __init__(self, env):
-        super().__init__()
-        self.env = env
-        for name in ("possible_agents", "metadata", "observation_spaces", "action_spaces"):
+# ---- guards: (layer, action) -> True when the call has been fully handled and must NOT be forwarded ----------
+def guard_reset_first(layer, what):
+    if not layer._state.get("has_reset"):
+        raise AssertionError(f"reset() needs to be called before {what}")
+    return False
+
+
+def guard_cycle_over(layer, action):
+    return not layer.agents                       # OrderEnforcingWrapper.step on an exhausted env is a no-op
+
+
+def guard_bounds(layer, action):
+    who = layer.agent_selection
+    ok = (action is None and finished(layer, who)) or layer.action_space(who).contains(action)
+    assert ok, "action is not in action space"
+    return False
+
+
+def guard_illegal(layer, action):
+    """TerminateIllegalWrapper.step: the mask seen by the last observe(agent_selection) decides."""
+    st, who = layer._state, layer.agent_selection
+    if st.get("seen") is None:
+        layer.observe(who)
+    mask, st["seen"] = st["seen"]["action_mask"], None
+    if st.get("ended"):
+        TRANSITIONS["dead_step"](layer, action)
+        return True
+    if finished(layer, who) or mask[action]:
+        return False                              # legal (or a regular dead step): forward
+    layer._cumulative_rewards[who] = 0
+    layer.terminations = dict.fromkeys(layer.agents, True)
+    layer.truncations = dict.fromkeys(layer.agents, True)
+    layer.rewards = dict.fromkeys(layer.truncations, 0)
+    layer.rewards[who] = float(st["illegal_reward"])
+    TRANSITIONS["accumulate"](layer)
+    TRANSITIONS["deads_first"](layer)
+    st["ended"] = True
+    return True
+
+
+RULES = {
+    "BaseWrapper": {},
+    "CaptureStdoutWrapper": {},
+    "TerminateIllegalWrapper": {"step": [guard_illegal], "remember_observation": True,
+                                "on_reset": {"ended": False, "seen": None}},
+    "AssertOutOfBoundsWrapper": {"step": [guard_bounds]},
+    "OrderEnforcingWrapper": {"step": [lambda l, a: guard_reset_first(l, "step"), guard_cycle_over],
+                              "observe": [lambda l, a: guard_reset_first(l, "observe")],
+                              "render": [lambda l, a: guard_reset_first(l, "render")],
+                              "agent_iter": [lambda l, a: guard_reset_first(l, "agent_iter")],
+                              "hidden_before_reset": ("rewards", "terminations", "truncations", "infos", "agent_selection",
+                                                      "num_agents", "agents"),
+                              "on_reset": {"has_reset": True}},
+}
+
+
+class _Layer(AECEnv):
+    RULE = "BaseWrapper"
+
+    def __init__(self, env, illegal_reward=None):
+        self.__dict__["_state"] = {"illegal_reward": illegal_reward}
+        self.__dict__["env"] = env
+        for name in STATIC:
             if hasattr(env, name):
                 setattr(self, name, getattr(env, name))
 
+    def _rule(self, key, default=()):
+        return RULES[self.RULE].get(key, default)
+
+    def _guards(self, op, arg=None):
+        return any(g(self, arg) for g in self._rule(op))
+
+    def _mirror(self):
+        for name in MIRRORED:
+            setattr(self, name, getattr(self.env, name))
+
     def __getattr__(self, name):
+        if name in self._rule("hidden_before_reset") and not self._state.get("has_reset"):
+            raise AttributeError(f"{name} cannot be accessed before reset")
         if name.startswith("_"):
             raise AttributeError(f"accessing private attribute '{name}' is prohibited")
         return getattr(self.env, name)
 
-    @property
-    def unwrapped(self):
-        return self.env.unwrapped
-
-    def _mirror(self):
-        for name in _MIRRORED:
-            setattr(self, name, getattr(self.env, name))
-
-    def close(self):
-        self.env.close()
-
-    def render(self):
-        return self.env.render()
+    unwrapped = property(lambda self: self.env.unwrapped)
 
     def reset(self, seed=None, return_info=False, options=None):
+        self._state.update(self._rule("on_reset", {}))
         self.env.reset(seed=seed, options=options)
         self._mirror()
 
-    def observe(self, agent):
-        return self.env.observe(agent)
-
     def step(self, action):
+        if self._guards("step", action):
+            return
         self.env.step(action)
         self._mirror()
+
+    def observe(self, agent):
+        self._guards("observe")
+        obs = self.env.observe(agent)
+        if self._rule("remember_observation", False) and agent == self.agent_selection:
+            self._state["seen"] = obs
+        return obs
+
+    def render(self):
+        self._guards("render")
+        return self.env.render()
+
+    def agent_iter(self, max_iter=2**63):
+        self._guards("agent_iter")
+        return super().agent_iter(max_iter)
+
+    def close(self):
+        self.env.close()
 
     def observation_space(self, agent):
         return self.env.observation_space(agent)
@@ -50,90 +133,12 @@ class BaseWrapper(AECEnv):
         return self.env.action_space(agent)
 
 
-class CaptureStdoutWrapper(BaseWrapper):
-    pass
+def _named(rule):
+    return type(rule, (_Layer,), {"RULE": rule, "__doc__": f"pettingzoo.utils.wrappers.{rule} (stand-in, rule-table driven)"})
 
 
-class TerminateIllegalWrapper(BaseWrapper):
-    def __init__(self, env, illegal_reward):
-        super().__init__(env)
-        self._illegal_value = illegal_reward
-        self._prev_obs = None
-
-    def reset(self, seed=None, return_info=False, options=None):
-        self._terminated = False
-        self._prev_obs = None
-        super().reset(seed=seed, options=options)
-
-    def observe(self, agent):
-        obs = super().observe(agent)
-        if agent == self.agent_selection:
-            self._prev_obs = obs
-        return obs
-
-    def step(self, action):
-        current = self.agent_selection
-        if self._prev_obs is None:
-            self.observe(current)
-        mask = self._prev_obs["action_mask"]
-        self._prev_obs = None
-        if self._terminated:
-            self._was_dead_step(action)
-        elif (not self.terminations[current] and not self.truncations[current] and not mask[action]):
-            self._cumulative_rewards[current] = 0
-            self.terminations = {a: True for a in self.agents}
-            self.truncations = {a: True for a in self.agents}
-            self.rewards = {a: 0 for a in self.truncations}
-            self.rewards[current] = float(self._illegal_value)
-            self._accumulate_rewards()
-            self._deads_step_first()
-            self._terminated = True
-        else:
-            super().step(action)
-
-
-class AssertOutOfBoundsWrapper(BaseWrapper):
-    def step(self, action):
-        sel = self.agent_selection
-        dead = self.terminations[sel] or self.truncations[sel]
-        assert (action is None and dead) or self.action_space(sel).contains(action), \
-            "action is not in action space"
-        super().step(action)
-
-
-class OrderEnforcingWrapper(BaseWrapper):
-    def __init__(self, env):
-        self._has_reset = False
-        super().__init__(env)
-
-    def __getattr__(self, name):
-        if name in ("rewards", "terminations", "truncations", "infos", "agent_selection",
-                    "num_agents", "agents"):
-            raise AttributeError(f"{name} cannot be accessed before reset")
-        return super().__getattr__(name)
-
-    def _need_reset(self, what):
-        if not self._has_reset:
-            raise AssertionError(f"reset() needs to be called before {what}")
-
-    def render(self):
-        self._need_reset("render")
-        return super().render()
-
-    def step(self, action):
-        self._need_reset("step")
-        if not self.agents:
-            return None
-        super().step(action)
-
-    def observe(self, agent):
-        self._need_reset("observe")
-        return super().observe(agent)
-
-    def agent_iter(self, max_iter=2**63):
-        self._need_reset("agent_iter")
-        return super().agent_iter(max_iter)
-
-    def reset(self, seed=None, return_info=False, options=None):
-        self._has_reset = True
-        super().reset(seed=seed, options=options)
+BaseWrapper = _named("BaseWrapper")
+CaptureStdoutWrapper = _named("CaptureStdoutWrapper")
+TerminateIllegalWrapper = _named("TerminateIllegalWrapper")
+AssertOutOfBoundsWrapper = _named("AssertOutOfBoundsWrapper")
+OrderEnforcingWrapper = _named("OrderEnforcingWrapper")

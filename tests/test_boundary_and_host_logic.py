@@ -218,3 +218,109 @@ def test_two_rank_gloo_statistics_all_reduce(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "OK" in res.stdout
+
+
+# ---- the wrapper stack, pinned by a literal transition table ----------------------------------
+# PettingZoo 1.22.3 is absent from the image, so the product's _aec.py and the test-side stand-ins (a rule-table
+# model, oracle/standins) are two independent statements of its published behaviour.  The table
+# below is a third one: hand-written expected `last()` tuples and bookkeeping for scripted calls, derived from
+# App. D, not from either implementation.  Both implementations must reproduce every row.
+# Scripted env: agents a, b; action 1 ends the game (a +1, b -1); action 2 is masked out (mask = [1, 1, 0]).
+_AEC_TABLE = [
+    # (call, argument)                 -> expected (agent_selection, agents, cumulative reward of the selection, terminated, truncated)
+    (("reset", None),                  ("a", ["a", "b"], 0, False, False)),
+    (("step", 0),                      ("b", ["a", "b"], 0, False, False)),
+    (("step", 1),                      ("a", ["a", "b"], 1, True, False)),     # b ended the game: a is served first, +1
+    (("step", None),                   ("b", ["b"], -1, True, False)),         # dead step removes a; b sees its -1
+    (("step", None),                   (None, [], None, None, None)),          # cycle over
+    (("reset", None),                  ("a", ["a", "b"], 0, False, False)),
+    (("step", 2),                      ("a", ["a", "b"], -1.0, True, True)),   # masked action: illegal-move termination, mover -1
+    (("step_raises", (0, ValueError)), ("a", ["a", "b"], -1.0, True, True)),   # a dead agent may only step(None)
+    (("step", None),                   ("b", ["b"], 0, True, True)),           # other agent: 0, also terminated AND truncated
+    (("step", None),                   (None, [], None, None, None)),
+    (("reset", None),                  ("a", ["a", "b"], 0, False, False)),
+    (("step", 0),                      ("b", ["a", "b"], 0, False, False)),
+    (("step", 2),                      ("a", ["a", "b"], 0, True, True)),      # illegal by b: dead agents are served in `agents` order
+    (("step", None),                   ("b", ["b"], -1.0, True, True)),
+    (("step_raises", (7, AssertionError)), ("b", ["b"], -1.0, True, True)),    # out of bounds (and not None) for a dead agent
+    (("step", None),                   (None, [], None, None, None)),
+]
+
+
+def _scripted_env(base, spaces, selector):
+    class Scripted(base):
+        metadata = {"name": "scripted"}
+
+        def __init__(self):
+            super().__init__()
+            self.possible_agents = ["a", "b"]
+            self.action_spaces = {x: spaces.Discrete(3) for x in self.possible_agents}
+            self.observation_spaces = {x: spaces.Dict({"action_mask": spaces.Box(0, 1, (3,), np.int8)})
+                                       for x in self.possible_agents}
+            self._sel = selector(self.possible_agents)
+
+        def reset(self, seed=None, return_info=False, options=None):
+            self.agents = self.possible_agents[:]
+            self.rewards = {x: 0 for x in self.agents}
+            self._cumulative_rewards = {x: 0 for x in self.agents}
+            self.terminations = {x: False for x in self.agents}
+            self.truncations = {x: False for x in self.agents}
+            self.infos = {x: {} for x in self.agents}
+            self._sel.reinit(self.agents)
+            self.agent_selection = self._sel.reset()
+
+        def observe(self, agent):
+            return {"action_mask": np.array([1, 1, 0], np.int8)}
+
+        def step(self, action):
+            if self.terminations[self.agent_selection]:
+                return self._was_dead_step(action)
+            nxt = self._sel.next()
+            if action == 1:
+                mover = self.agent_selection
+                self.rewards = {x: (-1 if x == mover else 1) for x in self.agents}
+                self.terminations = {x: True for x in self.agents}
+            self._cumulative_rewards[self.agent_selection] = 0
+            self.agent_selection = nxt
+            self._accumulate_rewards()
+
+    return Scripted()
+
+
+@pytest.mark.parametrize("impl", ["product_aec", "standin_model"])
+def test_aec_semantics_table(impl):
+    if impl == "product_aec":
+        from gobblet_rl_b200 import _aec as A, _spaces as S
+        base, sel, W = A.AECEnv, A.agent_selector, A
+    else:
+        import importlib
+        from oracle import reference_loader as RL
+        sys.path.insert(0, RL.STANDINS)
+        try:
+            pz = importlib.import_module("pettingzoo")
+            W = importlib.import_module("pettingzoo.utils.wrappers")
+            sel = importlib.import_module("pettingzoo.utils").agent_selector
+            S = importlib.import_module("gymnasium.spaces")
+        finally:
+            sys.path.remove(RL.STANDINS)
+        assert "standin" in pz.__version__
+        base = pz.AECEnv
+    env = W.OrderEnforcingWrapper(W.AssertOutOfBoundsWrapper(W.TerminateIllegalWrapper(_scripted_env(base, S, sel), -1)))
+    with pytest.raises(AssertionError):
+        env.step(0)                                            # OrderEnforcingWrapper: reset first
+    for row, ((call, arg), want) in enumerate(_AEC_TABLE):
+        if call == "reset":
+            env.reset()
+        elif call == "step":
+            env.step(arg)
+        else:
+            with pytest.raises(arg[1]):
+                env.step(arg[0])
+        sel_want, agents_want, rew_want, term_want, trunc_want = want
+        assert list(env.agents) == agents_want, (impl, row)
+        assert next(iter(env.agent_iter()), None) == (sel_want if agents_want else None), (impl, row)
+        if agents_want:
+            assert env.agent_selection == sel_want, (impl, row)
+            obs, rew, term, trunc, info = env.last()
+            assert (rew, term, trunc) == (rew_want, term_want, trunc_want) and type(rew) is type(rew_want), (impl, row, rew, term, trunc)
+            assert obs["action_mask"].tolist() == [1, 1, 0] and info == {}

@@ -19,5 +19,11 @@ for n in (1000, 37):
     gobblet_v1.greedy_actions(v.obs, v.mask, depth=2)
     sq, ag = v.squares()
     v.set_squares(sq, ag)
+    v.step_packed(acts)
+    act = torch.zeros(n, dtype=torch.int32, device="cuda")
+    from gobblet_rl_b200 import ops
+    ops.sample_legal(v.mask, 1, 0, 0, act)
+    v.rollout_random(6, ring=1, final=True, per_step=True)          # slots rewritten inside the launch (bulk-store ordering)
+    v.rollout_random(6, ring=2, block_hint=32)
 torch.cuda.synchronize()
 print("sanitizer case done")
