@@ -414,8 +414,9 @@ def measure_configs(a, ctx):
         vec, buf, col = collector(n5, T5, keep_final, base=rank * n5)
 
         def once():
-            col.collect()
-            col.roll()
+            col.collect()                             # fused: one launch, slot 0 re-emitted from the state (no roll() copy needed)
+            if not col.fused:
+                col.roll()
         ctx["sync_all"]()
         dt = device_time(once, 10)
         t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -154,9 +154,10 @@ class VecCollector:
 
     def _collect_fused(self):
         b, v, p = self.buf, self.vec, self.policy
-        ops.rollout_random(v.state, b.horizon, p.seed, p.env_id_base, p.step, b.obs[1:], b.mask[1:], b.rew,
-                           b.terminated.view(torch.uint8), b.agent_id[1:], b.act, b.final_obs, b.final_mask, v.stats,
-                           v.flags | ops.SLOT_FROM_ZERO, p.step_dev)
+        # slot 0 (what the policy saw before step 0) is emitted by the same launch from the state itself
+        ops.rollout_random(v.state, b.horizon, p.seed, p.env_id_base, p.step, b.obs, b.mask, b.rew,
+                           b.terminated.view(torch.uint8), b.agent_id, b.act, b.final_obs, b.final_mask, v.stats,
+                           v.flags | ops.SLOT_FROM_ZERO | ops.EMIT_INITIAL, p.step_dev)
         v._advance(b.horizon)
         p.advance(b.horizon)
         return b
@@ -174,7 +175,8 @@ class VecCollector:
         return b
 
     def roll(self):
-        """Make the last slot the first one of the next collection."""
+        """Make the last slot the first one of the next collection.  (A fused collection re-emits slot 0 itself from
+        the state the previous one left, so back-to-back fused collections do not need this copy.)"""
         b = self.buf
         b.obs[0].copy_(b.obs[-1]); b.mask[0].copy_(b.mask[-1]); b.agent_id[0].copy_(b.agent_id[-1])
 

@@ -205,6 +205,17 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
         const bool emit = p.obs_out != nullptr;
         const uint32_t opts = ((p.flags >> 8) & 3u) |        // GBL_MEASURE_SKIP_*_STORES
                               (p.ring >= p.T ? 0u : p.ring == 1 ? EMIT_REUSE_ALWAYS : EMIT_REUSE_RING);
+        const uint32_t initial = kAux && (p.flags & GBL_EMIT_INITIAL) ? 1u : 0u;
+        if (initial) {                          // trajectory-buffer layout: slot 0 = the observation before the first step
+            if (emit) {
+                stage_env(stage, cfg, lane, e, m0, m1);
+                __syncwarp();
+                emit_chunk<kStreaming>(stage, lane, p.obs_out + first * GBL_OBS_BYTES, p.mask_out + first * GBL_MASK_BYTES, nvalid, opts);
+                __syncwarp();
+            }
+            if (valid && p.agent_out) p.agent_out[g] = (uint8_t)e.agent;
+            slot = 1u;
+        }
 #pragma unroll 2
         for (int32_t t = 0; t < p.T; ++t) {     // two plies per trip: the own/opponent register swap becomes renaming
             const uint64_t s = step_base + (uint64_t)t;
@@ -223,8 +234,8 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
             if (kAux && p.final_obs_out) {      // the observation a same-step reset is about to replace
                 stage_env(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(stage, lane, p.final_obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
-                                       p.final_mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
+                emit_chunk<kStreaming>(stage, lane, p.final_obs_out + (int64_t)(slot - initial) * p.obs_slot_stride + first * GBL_OBS_BYTES,
+                                       p.final_mask_out + (int64_t)(slot - initial) * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
             if (r.term && same_step) {          // raw_env.reset: empty board, player_1 to move, every action legal
@@ -232,9 +243,9 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                 m0 = 0xFFFFFFFFu; m1 = 0x003FFFFFu;
             }
             if (kAux && valid) {
-                const int64_t o = (int64_t)slot * p.n + g;
-                if (p.rew_out) *reinterpret_cast<char2 *>(p.rew_out + 2 * o) = make_char2((signed char)r.r1, (signed char)r.r2);
-                if (p.term_out) p.term_out[o] = r.term;
+                const int64_t o = (int64_t)slot * p.n + g, oa = o - (int64_t)initial * p.n;   // [T+1] slots vs [T] slots
+                if (p.rew_out) *reinterpret_cast<char2 *>(p.rew_out + 2 * oa) = make_char2((signed char)r.r1, (signed char)r.r2);
+                if (p.term_out) p.term_out[oa] = r.term;
                 if (p.agent_out) p.agent_out[o] = (uint8_t)e.agent;
                 if (p.action_log) p.action_log[(int64_t)t * p.n + g] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
@@ -557,6 +568,8 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     if ((final_obs_out == nullptr) != (final_mask_out == nullptr) || (final_obs_out && !obs_out))
         return fail(GBL_E_INVALID, "gbl_rollout_random: final_obs_out and final_mask_out go together and need obs_out / mask_out");
     if (ring < 1) return fail(GBL_E_INVALID, "gbl_rollout_random: ring must be >= 1");
+    if ((flags & GBL_EMIT_INITIAL) && (!(flags & GBL_SLOT_FROM_ZERO) || ring < T + 1))
+        return fail(GBL_E_INVALID, "gbl_rollout_random: GBL_EMIT_INITIAL needs GBL_SLOT_FROM_ZERO and ring >= T + 1");
     if (obs_out) {
         if (!aligned16(obs_out) || !aligned16(mask_out) || (obs_slot_stride & 15) || (mask_slot_stride & 15))
             return fail(GBL_E_INVALID, "gbl_rollout_random: obs/mask bases and slot strides must be multiples of 16 bytes");
@@ -575,7 +588,7 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     const bool plain = flags & GBL_STORE_DEFAULT_POLICY;
     cudaStream_t s = (cudaStream_t)stream;
     const int block = rollout_block_for(n, flags);
-    const bool aux = rew_out || term_out || agent_out || action_log || final_obs_out;
+    const bool aux = rew_out || term_out || agent_out || action_log || final_obs_out || (flags & GBL_EMIT_INITIAL);
 #define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
     do {                                                                            \
         if (aux) launch_rollout_b<F, S, true>(p, block, s);                         \

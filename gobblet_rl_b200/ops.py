@@ -17,6 +17,7 @@ AUTORESET_OFF, AUTORESET_SAME_STEP, AUTORESET_NEXT_STEP = 0 << 1, 1 << 1, 2 << 1
 STORE_DEFAULT_POLICY = 0x8
 ACTION_SKIP_255 = 0x10
 SLOT_FROM_ZERO = 0x20
+EMIT_INITIAL = 0x40
 BLOCK_HINT_SHIFT = 12
 REC_WORDS = 6                      # packed wire format: 6 x u32 = 24 bytes per env (include/gobblet_b200.h)
 ABI_VERSION = 3
@@ -195,17 +196,19 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
     aux = [t for t in (rew_out, term_out, agent_out) if t is not None]
     if obs_out is None and aux:
         ring = aux[0].shape[0]
+    initial = 1 if flags & EMIT_INITIAL else 0      # [T+1] observation / agent slots next to [T] reward / flag slots
     for t in aux:
-        if t.shape[0] != ring:
+        if t.shape[0] != ring - (0 if t is agent_out else initial):
             raise GobbletError("per-step outputs must share one ring length (that of obs_out when it is given)")
-    _need_bytes("rew_out", rew_out, ring * n * 2); _need_bytes("term_out", term_out, ring * n)
+    _need_bytes("rew_out", rew_out, (ring - initial) * n * 2); _need_bytes("term_out", term_out, (ring - initial) * n)
     _need_bytes("agent_out", agent_out, ring * n); _need_bytes("action_log", action_log, T * n)
     if (final_obs_out is None) != (final_mask_out is None):
         raise GobbletError("final_obs_out / final_mask_out go together")
     if final_obs_out is not None:
         if obs_out is None or not (final_obs_out.is_cuda and final_mask_out.is_cuda):
             raise GobbletError("final_obs_out / final_mask_out need obs_out / mask_out and must be CUDA tensors")
-        if (final_obs_out.shape != obs_out.shape or final_mask_out.shape != mask_out.shape or final_obs_out.stride(0) != so
+        if (final_obs_out.shape[1:] != obs_out.shape[1:] or final_mask_out.shape[1:] != mask_out.shape[1:]
+                or final_obs_out.shape[0] != ring - initial or final_mask_out.shape[0] != ring - initial or final_obs_out.stride(0) != so
                 or final_mask_out.stride(0) != sm or final_obs_out.element_size() != 1 or final_mask_out.element_size() != 1
                 or not final_obs_out[0].is_contiguous() or not final_mask_out[0].is_contiguous()):
             raise GobbletError("final_obs_out / final_mask_out must match obs_out / mask_out in shape and slot stride")

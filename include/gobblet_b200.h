@@ -60,6 +60,10 @@ extern "C" {
                                          every other value outside [0,54) is an illegal move */
 #define GBL_SLOT_FROM_ZERO 0x20u      /* gbl_rollout_random: step t goes to ring slot t % ring (not (step_base+t) % ring):
                                          the launch writes straight into the slots of a caller's trajectory buffer */
+#define GBL_EMIT_INITIAL 0x40u        /* gbl_rollout_random, with GBL_SLOT_FROM_ZERO: slot 0 of obs_out / mask_out / agent_out receives the
+                                         observation of the state as loaded, step t goes to slot t+1 (ring >= T+1); rew_out /
+                                         term_out / final_*_out keep T slots indexed by t -- the [T+1] / [T] layout of a
+                                         trajectory buffer, filled without a separate observe or copy launch */
 #define GBL_BLOCK_HINT_SHIFT 12       /* gbl_rollout_random: bits 12-14 = threads per block, 0 auto, 1..4 = 32/64/128/256 (tuning aid) */
 #define GBL_MEASURE_SKIP_OBS_STORES 0x100u  /* gbl_rollout_random only: measurement aid, do everything but the obs stores */
 #define GBL_MEASURE_SKIP_MASK_STORES 0x200u /* gbl_rollout_random only: measurement aid, do everything but the mask stores */

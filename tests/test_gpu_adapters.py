@@ -239,7 +239,8 @@ def test_host_vec_env_packed_consumer(ad):
 
 def test_fused_collection_equals_step_by_step_collection(ad):
     """The built-in masked-uniform policy collects in ONE launch (fused rollout writing into the buffer slots,
-    terminal observations included); it must fill the buffer exactly like sample_legal + step per step."""
+    slot 0 and the terminal observations included); it must fill the buffer exactly like sample_legal + step
+    per step."""
     from gobblet_rl_b200 import gobblet_v1
     n, T = 3000, 12
     bufs = []
@@ -253,8 +254,19 @@ def test_fused_collection_equals_step_by_step_collection(ad):
             col.collect(); col.roll()
         assert vec.kernel_launches - launches == (2 if fused else 2 * T)
         bufs.append((vec, buf, col))
-    (va, a, _), (vb, b, _) = bufs
-    for name in ("obs", "mask", "agent_id", "act", "rew", "terminated", "truncated", "final_obs", "final_mask"):
+    (va, a, ca), (vb, b, cb) = bufs
+    fields = ("obs", "mask", "agent_id", "act", "rew", "terminated", "truncated", "final_obs", "final_mask")
+    for name in fields:
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(va.state, vb.state) and va.stats.tolist() == vb.stats.tolist() and a.terminated.any()
-    assert va.step_count == vb.step_count == 2 * T
+    # a fused collection re-emits slot 0 from the state itself: no roll() needed between collections
+    last = (a.obs[-1].clone(), a.mask[-1].clone(), a.agent_id[-1].clone())
+    ca.collect(); a.obs[0].fill_(7); a.mask[0].fill_(7); a.agent_id[0].fill_(7)          # scribble over slot 0, no roll()
+    cb.collect(); cb.roll()
+    va2 = va.state.clone()
+    ca.collect()
+    cb.collect()
+    for name in fields:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert not torch.equal(va2, va.state) and torch.equal(va.state, vb.state)
+    assert va.step_count == vb.step_count == 4 * T and not torch.equal(last[0], a.obs[0])
