@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""BASELINE config 2 regime (a few thousand lockstep envs: latency-bound, the 0.7 MB of output per step stays in
+L2): microseconds per lockstep step of the fused rollout for every block size (32 / 64 / 128 / 256 threads) and,
+for the small blocks, with the observation image leaving through the copy engine (TMA bulk store) or through a
+lane copy (LDS.128 -> STG.128).  Prints one JSON object; the best variant per size is what
+`rollout_block_for` / the default flags in gobblet_engine.cu wire in."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gobblet_rl_b200 import gobblet_v1  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    out = {}
+    for n in (1024, 4096, 16384, 65536):
+        T = 4096 if n <= 16384 else 512
+        vec = gobblet_v1.vec_env(n, device=dev, seed=0)
+        res = {}
+        for hint in (0, 32, 64, 128, 256):
+            for no_bulk in ((False, True) if hint in (0, 32, 64) else (False,)):
+                for _ in range(2):
+                    vec.rollout_random(T, ring=4, block_hint=hint, no_bulk=no_bulk)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(3):
+                    vec.rollout_random(T, ring=4, block_hint=hint, no_bulk=no_bulk)
+                b.record()
+                torch.cuda.synchronize()
+                res[f"{'auto' if hint == 0 else hint}{'_lanecopy' if no_bulk else '_bulk'}"] = a.elapsed_time(b) * 1e3 / 3 / T
+        out[str(n)] = {"us_per_lockstep_step": res, "hbm_time_us": n * 171 / 6552.6e9 * 1e6,
+                       "best": min(res, key=res.get), "env_steps_per_s_best": n / (min(res.values()) * 1e-6)}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

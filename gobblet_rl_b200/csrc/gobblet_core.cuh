@@ -363,6 +363,7 @@ __device__ __forceinline__ void fence_smem_for_bulk() {    // generic-proxy smem
 
 // stage: all 32 lanes of the warp must call (shuffle inside).  stage = this warp's STAGE_BYTES.
 // The caller puts a __syncwarp() between stage_env and emit_chunk and one after emit_chunk.
+template <bool kBulk = kBulkStore>
 __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint32_t lane, const Env &e,
                                           uint32_t m0, uint32_t m1) {
     uint8_t *mine = stage + 117u * lane;
@@ -381,7 +382,7 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
     if (lane == 0) prev = 0;
     mbits[c.mfo] = v0 | prev;
     if (c.mn2) mbits[c.mfo + 1] = v1;
-    if (kBulkStore) fence_smem_for_bulk();
+    if (kBulk) fence_smem_for_bulk();
 }
 
 // copy / expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this
@@ -391,7 +392,7 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
 // must have COMPLETED (not merely been read) before the next one is issued -- that is the group before the
 // newest one when ring >= 2, the newest one when ring == 1.
 constexpr uint32_t EMIT_REUSE_RING = 4u, EMIT_REUSE_ALWAYS = 8u;
-template <bool kStreaming>
+template <bool kStreaming, bool kBulk = kBulkStore>
 __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t *obs_chunk,
                                            int8_t *mask_chunk, int nvalid, uint32_t opts = 0u) {
     const uint32_t skip = opts & 3u;
@@ -399,7 +400,7 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
     const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage + OBS_IMG_BYTES);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid == 32) {
-        if (kBulkStore) {
+        if (kBulk) {
             if (lane == 0 && !(skip & 1u)) {
                 if (opts & EMIT_REUSE_ALWAYS) bulk_store_wait_all();
                 else if (opts & EMIT_REUSE_RING) bulk_store_wait_all_but_latest();
@@ -421,7 +422,7 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
             uint32_t q = lane + 32u * i;
             if ((i < 3 || q < MASK_VEC) && !(skip & 2u)) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
         }
-        if (kBulkStore) {                      // re-zero the image once the copy engine has read it
+        if (kBulk) {                           // re-zero the image once the copy engine has read it
             if (lane == 0) bulk_store_wait_read();
             __syncwarp();
 #pragma unroll

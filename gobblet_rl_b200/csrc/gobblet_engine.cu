@@ -177,7 +177,9 @@ struct RolloutParams {
 //        a large top).  The one exception is an env that ARRIVES finished (state imported from an "off" /
 //        "next_step" run): its first step only resets it, exactly as the general path and the oracle do.
 // kAux:  any of rew_out / term_out / agent_out / action_log / final_*_out is requested (compiled out otherwise)
-template <bool kFast, bool kStreaming, bool kAux, int kBlock>
+// kBulk: the observation image leaves through the copy engine (TMA bulk store); false = 32-lane LDS.128 -> STG.128 copy,
+//        which has no asynchronous completion to wait for (small batches: one warp per scheduler, latency-bound)
+template <bool kFast, bool kStreaming, bool kAux, int kBlock, bool kBulk>
 __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutParams p) {
     extern __shared__ __align__(16) uint8_t stage_all[];      // (kBlock/32) * STAGE_BYTES, one staging area per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -208,9 +210,9 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
         const uint32_t initial = kAux && (p.flags & GBL_EMIT_INITIAL) ? 1u : 0u;
         if (initial) {                          // trajectory-buffer layout: slot 0 = the observation before the first step
             if (emit) {
-                stage_env(stage, cfg, lane, e, m0, m1);
+                stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(stage, lane, p.obs_out + first * GBL_OBS_BYTES, p.mask_out + first * GBL_MASK_BYTES, nvalid, opts);
+                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + first * GBL_OBS_BYTES, p.mask_out + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
             if (valid && p.agent_out) p.agent_out[g] = (uint8_t)e.agent;
@@ -232,9 +234,9 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
             occupancy(e, u, up);
             legal_mask(e.xo, e.yo, u, up, m0, m1);
             if (kAux && p.final_obs_out) {      // the observation a same-step reset is about to replace
-                stage_env(stage, cfg, lane, e, m0, m1);
+                stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(stage, lane, p.final_obs_out + (int64_t)(slot - initial) * p.obs_slot_stride + first * GBL_OBS_BYTES,
+                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.final_obs_out + (int64_t)(slot - initial) * p.obs_slot_stride + first * GBL_OBS_BYTES,
                                        p.final_mask_out + (int64_t)(slot - initial) * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
@@ -250,15 +252,15 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                 if (p.action_log) p.action_log[(int64_t)t * p.n + g] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
             if (emit) {
-                stage_env(stage, cfg, lane, e, m0, m1);
+                stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
+                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
                                        p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
         }
-        if (kBulkStore && lane == 0) bulk_store_wait_all();
+        if (kBulk && kBulkStore && lane == 0) bulk_store_wait_all();
         if (valid) p.state[g] = env_pack(e);
         if (kFast) {   // every step but a reset-only first one was a live, legal step: these follow from the step count
             st.steps = live_steps;
@@ -469,34 +471,36 @@ static int check_launch(const char *what) {
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
 
-// threads per block of the fused rollout: 256 once the grid fills the machine, smaller blocks for small
-// batches so that >= 148 SMs (x 4 schedulers) get a warp each (BASELINE config 2, 4096 envs: latency-bound)
+// threads per block of the fused rollout: 256 once the grid fills the machine; one-warp blocks for small batches
+// so that every SM (x 4 schedulers) gets warps and the hardware spreads them evenly (BASELINE config 2, 4096
+// envs, is latency-bound: ~1500 cycles of dependent instructions per warp-step).  Measured on a B200
+// (benchmarks/sweep_small_batch.py, profiles/r2_sweep_small_batch.json): 32-thread blocks are fastest up to 64 Ki
+// envs; below ~5 Ki envs copying the observation image with the lanes beats the copy engine by 3 %.
 static int rollout_block_for(int64_t n, uint32_t flags) {
     const uint32_t hint = (flags >> GBL_BLOCK_HINT_SHIFT) & 7u;
     if (hint) return hint == 1 ? 32 : hint == 2 ? 64 : hint == 3 ? 128 : 256;
     const int64_t warps = (n + 31) / 32;
-    if (warps <= 2 * 148) return 32;       // at most ~2 warps per SM anyway: spread them
-    if (warps <= 8 * 148) return 64;
+    if (warps <= 16 * 148) return 32;
     if (warps <= 32 * 148) return 128;
     return 256;
 }
 
-template <bool F, bool S, bool A, int B>
+template <bool F, bool S, bool A, int B, bool K>
 static void launch_rollout(const RolloutParams &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.n + B - 1) / B);
     const size_t smem = (size_t)(B / 32) * STAGE_BYTES;
-    rollout_kernel<F, S, A, B><<<grid, B, smem, s>>>(p);
+    rollout_kernel<F, S, A, B, K><<<grid, B, smem, s>>>(p);
 }
 template <bool F, bool S, bool A>
-static void launch_rollout_b(const RolloutParams &p, int block, cudaStream_t s) {
+static void launch_rollout_b(const RolloutParams &p, int block, bool bulk, cudaStream_t s) {
     if constexpr (!S) {
-        launch_rollout<F, S, A, 256>(p, s);                      // plain stores: measurement aid, one size
+        launch_rollout<F, S, A, 256, true>(p, s);                // plain stores: measurement aid, one size
     } else {
         switch (block) {
-            case 32: return launch_rollout<F, S, A, 32>(p, s);
-            case 64: return launch_rollout<F, S, A, 64>(p, s);
-            case 128: return launch_rollout<F, S, A, 128>(p, s);
-            default: return launch_rollout<F, S, A, 256>(p, s);
+            case 32: return bulk ? launch_rollout<F, S, A, 32, true>(p, s) : launch_rollout<F, S, A, 32, false>(p, s);
+            case 64: return bulk ? launch_rollout<F, S, A, 64, true>(p, s) : launch_rollout<F, S, A, 64, false>(p, s);
+            case 128: return launch_rollout<F, S, A, 128, true>(p, s);
+            default: return launch_rollout<F, S, A, 256, true>(p, s);
         }
     }
 }
@@ -588,11 +592,13 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     const bool plain = flags & GBL_STORE_DEFAULT_POLICY;
     cudaStream_t s = (cudaStream_t)stream;
     const int block = rollout_block_for(n, flags);
+    // lane copy instead of the copy engine: on request, or by default when there is at most one warp per SM
+    const bool bulk = !((flags & GBL_NO_BULK_STORE_HINT) || (!((flags >> GBL_BLOCK_HINT_SHIFT) & 7u) && n <= 148 * 32));
     const bool aux = rew_out || term_out || agent_out || action_log || final_obs_out || (flags & GBL_EMIT_INITIAL);
 #define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
     do {                                                                            \
-        if (aux) launch_rollout_b<F, S, true>(p, block, s);                         \
-        else launch_rollout_b<F, S, false>(p, block, s);                            \
+        if (aux) launch_rollout_b<F, S, true>(p, block, bulk, s);                   \
+        else launch_rollout_b<F, S, false>(p, block, bulk, s);                      \
     } while (0)
     if (fast) {
         if (plain) GBL_LAUNCH_ROLLOUT(true, false);

@@ -103,7 +103,7 @@ class VecEnv:
         self.kernel_launches += 1
 
     def rollout_random(self, T: int, ring: int = 1, emit: bool = True, per_step: bool = False,
-                       log_actions: bool = False, final: bool = False, block_hint: int = 0):
+                       log_actions: bool = False, final: bool = False, block_hint: int = 0, no_bulk: bool = False):
         """T fused lockstep steps with uniform random legal actions (example_basic.py:50-67) in ONE launch.
 
         emit      write the next observation + mask of every step to ring slot (step % ring)
@@ -127,7 +127,7 @@ class VecEnv:
         if log_actions:
             log = torch.zeros((T, n), dtype=torch.uint8, device=dev)
             out["actions"] = log
-        hint = {0: 0, 32: 1, 64: 2, 128: 3, 256: 4}[int(block_hint)] << ops.BLOCK_HINT_SHIFT
+        hint = ({0: 0, 32: 1, 64: 2, 128: 3, 256: 4}[int(block_hint)] << ops.BLOCK_HINT_SHIFT) | (ops.NO_BULK_STORE_HINT if no_bulk else 0)
         self._launch_rollout(T, obs_out, mask_out, rew_out, term_out, agent_out, log, fobs, fmask, self.flags | hint)
         return out
 

@@ -466,9 +466,10 @@ def test_rollout_block_sizes_and_short_rings_agree(gv1, n):
     T = 24
     ref = gv1.vec_env(n, seed=6)
     base = ref.rollout_random(T, ring=T, per_step=True, log_actions=True, final=True)
-    for hint, ring in ((32, T), (64, T), (128, 2), (256, 1), (0, 3), (32, 1)):
+    for hint, ring, no_bulk in ((32, T, False), (64, T, False), (128, 2, False), (256, 1, False), (0, 3, False), (32, 1, False),
+                                (32, T, True), (64, 2, True), (0, 1, True)):
         v = gv1.vec_env(n, seed=6)
-        out = v.rollout_random(T, ring=ring, per_step=True, log_actions=True, final=True, block_hint=hint)
+        out = v.rollout_random(T, ring=ring, per_step=True, log_actions=True, final=True, block_hint=hint, no_bulk=no_bulk)
         assert torch.equal(out["actions"], base["actions"]) and torch.equal(v.state, ref.state) and torch.equal(v.stats, ref.stats)
         for s in range(max(0, T - ring), T):
             for key in ("obs", "mask", "final_obs", "final_mask", "rew", "terminated", "agent_id"):
