@@ -154,8 +154,25 @@ def main():
     out["collect_mlp_policy_c5"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt,
                                     "env_steps_per_s_cuda_graph": n5 * T5 / dt_graph, "buffer_bytes": buf.nbytes(),
                                     "illegal_moves": int(v5.stats[5]), "note": "includes fp16 MLP inference + masked eps-greedy in torch"}
-    dt = timed(lambda: adapters.VecCollector(v5, adapters.RandomLegalPolicy(seed=3), buf).collect(), 10)
-    out["collect_random_policy"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt}
+    col_f = adapters.VecCollector(v5, adapters.RandomLegalPolicy(seed=3), buf)
+    dt = timed(col_f.collect, 10)
+    col_u = adapters.VecCollector(v5, adapters.RandomLegalPolicy(seed=3), buf, fused=False)
+    dt_u = timed(lambda: (col_u.collect(), col_u.roll()), 10)
+    out["collect_random_policy"] = {"envs": n5, "steps": T5, "env_steps_per_s": n5 * T5 / dt, "launches": 1,
+                                    "env_steps_per_s_unfused_sample_step_per_step": n5 * T5 / dt_u,
+                                    "note": "fused = ONE rollout launch writing into the buffer slots (incl. terminal observations)"}
+    # -- masked-uniform sampler alone (coalesced 128-bit mask loads), 2^20 rows ---------------------------------
+    from gobblet_rl_b200 import ops
+    act = torch.zeros(n, dtype=torch.int32, device=dev)
+    dt = timed(lambda: ops.sample_legal(vec.mask, 1, 0, 0, act), 50)
+    out["sample_legal_kernel"] = {"rows": n, "rows_per_s": n / dt, "us_per_launch": dt * 1e6,
+                                  "achieved_gbs": n * (54 + 4) / dt / 1e9, "frac_of_peak": n * 58 / dt / 1e9 / peak}
+    # -- packed wire format step (24-byte records), device resident -------------------------------------------
+    rec = torch.zeros((n, 6), dtype=torch.int32, device=dev)
+    a8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+    dt = timed(lambda: vec.step_packed(a8, rec=rec), 50)
+    out["step_packed_kernel"] = {"envs": n, "env_steps_per_s": n / dt, "us_per_launch": dt * 1e6,
+                                 "achieved_gbs": n * (32 + 1 + 24) / dt / 1e9, "frac_of_peak": n * 57 / dt / 1e9 / peak}
     # -- the drop-in facade: gobblet_v1.env() driven by the reference's own loop (example_basic.py:50-67) ------
     import time
 
