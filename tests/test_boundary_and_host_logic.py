@@ -295,14 +295,12 @@ def test_aec_semantics_table(impl):
     else:
         import importlib
         from oracle import reference_loader as RL
-        sys.path.insert(0, RL.STANDINS)
-        try:
-            pz = importlib.import_module("pettingzoo")
-            W = importlib.import_module("pettingzoo.utils.wrappers")
-            sel = importlib.import_module("pettingzoo.utils").agent_selector
-            S = importlib.import_module("gymnasium.spaces")
-        finally:
-            sys.path.remove(RL.STANDINS)
+        if RL.STANDINS not in sys.path:                        # left in place, exactly as reference_loader does
+            sys.path.insert(0, RL.STANDINS)
+        pz = importlib.import_module("pettingzoo")
+        W = importlib.import_module("pettingzoo.utils.wrappers")
+        sel = importlib.import_module("pettingzoo.utils").agent_selector
+        S = importlib.import_module("gymnasium.spaces")
         assert "standin" in pz.__version__
         base = pz.AECEnv
     env = W.OrderEnforcingWrapper(W.AssertOutOfBoundsWrapper(W.TerminateIllegalWrapper(_scripted_env(base, S, sel), -1)))
