@@ -70,20 +70,26 @@ def main():
     h_log = torch.zeros(log.shape, dtype=torch.uint8, pin_memory=True)
     h_log.copy_(log)
     res = {}
-    for name, kw in [("dense_chunks2", dict(wire="dense", chunks=2)),
-                     ("packed_chunks1", dict(wire="packed", chunks=1)), ("packed_chunks4", dict(wire="packed", chunks=4)),
-                     ("packed_chunks8", dict(wire="packed", chunks=8)), ("packed_chunks16", dict(wire="packed", chunks=16)),
-                     ("packed_chunks8_threads4", dict(wire="packed", chunks=8, host_threads=4)),
-                     ("packed_chunks8_threads8", dict(wire="packed", chunks=8, host_threads=8)),
-                     ("packed_chunks8_noexpand", dict(wire="packed", chunks=8, expand=False))]:
-        if kw.get("host_threads", 0) > cores:
-            continue
-        host = gobblet_v1.HostVecEnv(n, device=dev, seed=1, **kw)
-        dt = run(host, h_log, W, K, dev)
-        assert torch.equal(host.env.state, logger.state), name
-        res[name] = {"env_steps_per_s": n / dt, "ms_per_step": dt * 1e3, "pcie_gbs": host.d2h_bytes_per_step / dt / 1e9,
-                     "host_gbs": (host.host_bytes_per_step if host.expand else host.d2h_bytes_per_step) / dt / 1e9}
-        del host
+    variants = [("dense_chunks2", dict(wire="dense", chunks=2)), ("packed_geometric_schedule", dict(wire="packed")),
+                ("packed_chunks1", dict(wire="packed", chunks=1)), ("packed_chunks4", dict(wire="packed", chunks=4)),
+                ("packed_chunks8", dict(wire="packed", chunks=8)), ("packed_chunks16", dict(wire="packed", chunks=16)),
+                ("packed_chunks32", dict(wire="packed", chunks=32)),
+                ("packed_chunks8_threads4", dict(wire="packed", chunks=8, host_threads=4)),
+                ("packed_chunks8_threads8", dict(wire="packed", chunks=8, host_threads=8)),
+                ("packed_chunks8_threads12", dict(wire="packed", chunks=8, host_threads=12)),
+                ("packed_chunks8_noexpand", dict(wire="packed", chunks=8, expand=False))]
+    for rep in range(2):                                  # two rounds: the host side is noisy
+        for name, kw in variants:
+            if kw.get("host_threads", 0) > cores:
+                continue
+            host = gobblet_v1.HostVecEnv(n, device=dev, seed=1, **kw)
+            dt = run(host, h_log, W, K, dev)
+            assert torch.equal(host.env.state, logger.state), name
+            r = {"env_steps_per_s": n / dt, "ms_per_step": dt * 1e3, "pcie_gbs": host.d2h_bytes_per_step / dt / 1e9,
+                 "host_gbs": (host.host_bytes_per_step if host.expand else host.d2h_bytes_per_step) / dt / 1e9}
+            if name not in res or r["env_steps_per_s"] > res[name]["env_steps_per_s"]:
+                res[name] = r
+            del host
     # store mode of the expander: staged + non-temporal (default) vs direct regular stores
     ops.LIB.gbl_host_set_store_mode(1)
     host = gobblet_v1.HostVecEnv(n, device=dev, seed=1, wire="packed", chunks=8)

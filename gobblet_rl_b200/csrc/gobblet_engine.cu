@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/gobblet_b200.h"
 #include "gobblet_core.cuh"
@@ -13,6 +15,7 @@ extern "C" {
 void gblh_job_begin(const uint32_t *rec, int64_t n, int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated,
                     uint8_t *truncated, uint8_t *agent_id, int32_t nthreads);
 void gblh_job_publish(int64_t ready_envs);
+int gblh_job_try_one(void);
 void gblh_job_finish(void);
 }
 
@@ -689,6 +692,21 @@ int gbl_host_unpack_chunked(const uint32_t *rec, int64_t n, int32_t nchunks, con
     return rc;
 }
 
+// measurement aid: wall-clock marks of the last gbl_step_host call of this thread (seconds since its entry):
+// [0] enqueue done, [1 .. nchunks] chunk c published, [nchunks + 1] expansion finished
+static thread_local double g_marks[66];
+static thread_local int g_nmarks = 0;
+static inline double now_s() {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+int gbl_host_last_timing(double *out, int32_t cap) {
+    const int k = g_nmarks < cap ? g_nmarks : cap;
+    for (int i = 0; i < k; ++i) out[i] = g_marks[i];
+    return g_nmarks;
+}
+
 int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t flags, uint8_t *d_actions, uint32_t *d_rec,
                   uint32_t *h_rec, int32_t nchunks, const int64_t *chunk_end, void *stream, void *const *events,
                   int8_t *obs, int8_t *mask, int8_t *rew2, uint8_t *terminated, uint8_t *truncated, uint8_t *agent_id,
@@ -704,6 +722,9 @@ int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t 
     if ((flags & GBL_AUTORESET_MASK) == GBL_AUTORESET_MASK) return fail(GBL_E_INVALID, "gbl_step_host: bad autoreset mode");
     cudaStream_t s = (cudaStream_t)stream;
     const bool expand = obs != nullptr;
+    const double t_entry = now_s();
+    const bool mark = nchunks <= 64;
+    g_nmarks = 0;
     if (expand) gblh_job_begin(h_rec, n, obs, mask, rew2, terminated, truncated, agent_id, nthreads);   // workers spin on `ready`
     // one stream: actions H2D -> ONE step launch (packed records) -> the records D2H chunk by chunk, an event behind
     // each chunk.  While the later copies are still being enqueued, chunks that have already landed are published
@@ -719,18 +740,30 @@ int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, uint32_t 
         if (b > a) cudaMemcpyAsync(h_rec + 6 * a, d_rec + 6 * a, (size_t)(b - a) * 24, cudaMemcpyDeviceToHost, s);
         cudaEventRecord((cudaEvent_t)events[c], s);
         a = b;
-        while (expand && published < c && cudaEventQuery((cudaEvent_t)events[published]) == cudaSuccess)
+        while (expand && published < c && cudaEventQuery((cudaEvent_t)events[published]) == cudaSuccess) {
             gblh_job_publish(chunk_end[published++]);
+            if (mark) g_marks[published] = now_s() - t_entry;
+        }
     }
-    for (; published < nchunks; ++published) {       // wait for the rest in order
-        cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[published]);
+    if (mark) g_marks[0] = now_s() - t_entry;
+    static const int main_helps = getenv("GBL_HOST_MAIN_HELPS") ? atoi(getenv("GBL_HOST_MAIN_HELPS")) : 0;
+    while (published < nchunks) {                    // the rest in order
+        cudaError_t e = (expand && main_helps) ? cudaEventQuery((cudaEvent_t)events[published])
+                                               : cudaEventSynchronize((cudaEvent_t)events[published]);
+        if (e == cudaErrorNotReady) {                // (experiment) between two polls this thread expands too
+            if (!gblh_job_try_one()) __builtin_ia32_pause();
+            continue;
+        }
         if (e != cudaSuccess && rc == 0) {
             snprintf(g_err, sizeof(g_err), "gbl_step_host: %s", cudaGetErrorString(e));
             rc = GBL_E_CUDA;
         }
         if (expand) gblh_job_publish(chunk_end[published]);
+        ++published;
+        if (mark) g_marks[published] = now_s() - t_entry;
     }
     if (expand) gblh_job_finish();
+    if (mark) { g_marks[nchunks + 1] = now_s() - t_entry; g_nmarks = nchunks + 2; }
     return rc;
 }
 

@@ -277,6 +277,21 @@ void gblh_job_begin(const uint32_t *rec, int64_t n, int8_t *obs, int8_t *mask, i
 
 void gblh_job_publish(int64_t ready_envs) { atomic_store_explicit(&P.ready, ready_envs, memory_order_release); }
 
+/* The publishing thread helps between two event polls: expand ONE block, but only one that is already ready (it must
+ * never wait for a block, since it is the thread that makes blocks ready).  Returns 1 if a block was expanded. */
+int gblh_job_try_one(void) {
+    const gblh_job *j = &P.job;
+    int64_t k = atomic_load_explicit(&P.next, memory_order_relaxed);
+    const int64_t items = (j->n + GBLH_BLOCK - 1) / GBLH_BLOCK;
+    if (k >= items) return 0;
+    const int64_t a = k * GBLH_BLOCK, b = a + GBLH_BLOCK < j->n ? a + GBLH_BLOCK : j->n;
+    if (atomic_load_explicit(&P.ready, memory_order_acquire) < b) return 0;
+    if (!atomic_compare_exchange_strong_explicit(&P.next, &k, k + 1, memory_order_relaxed, memory_order_relaxed)) return 0;
+    if (P.simd) expand_avx512(j, a, b, P.store_mode);
+    else expand_table(j, a, b);
+    return 1;
+}
+
 void gblh_job_finish(void) {
     job_join();
     pthread_mutex_unlock(&P.api);

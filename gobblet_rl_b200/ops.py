@@ -56,6 +56,7 @@ def _load():
         "gbl_step_host": (C.c_int, [vp, vp, i64, u32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
         "gbl_host_fill": (C.c_int, [vp, i64, i32, i32]),
         "gbl_host_threads": (C.c_int, [i32]),
+        "gbl_host_last_timing": (C.c_int, [vp, i32]),
         "gbl_host_simd": (C.c_int, []),
         "gbl_host_set_store_mode": (C.c_int, [i32]),
         "gbl_sample_legal": (C.c_int, [vp, u64, u64, u64, vp, vp, i64, vp]),
@@ -75,7 +76,7 @@ LIB, LIB_PATH = _load()
 EXPORTED_SYMBOLS = ("gbl_abi_version", "gbl_last_error", "gbl_reset", "gbl_reset_masked", "gbl_observe",
                     "gbl_step", "gbl_rollout_random", "gbl_sample_legal", "gbl_greedy", "gbl_export_squares",
                     "gbl_import_squares", "gbl_step_packed", "gbl_observe_packed", "gbl_host_unpack",
-                    "gbl_host_unpack_chunked", "gbl_step_host", "gbl_host_fill", "gbl_host_threads", "gbl_host_simd",
+                    "gbl_host_unpack_chunked", "gbl_step_host", "gbl_host_last_timing", "gbl_host_fill", "gbl_host_threads", "gbl_host_simd",
                     "gbl_host_set_store_mode")
 
 
@@ -355,6 +356,13 @@ def host_fill(t: torch.Tensor, threads: int = 0, mode: int = 0):
     if t.is_cuda or not t.is_contiguous():
         raise GobbletError("host_fill needs a contiguous host tensor")
     _check(LIB.gbl_host_fill(_ptr(t), t.numel() * t.element_size(), threads, mode))
+
+
+def host_last_timing():
+    """Marks of the calling thread's last gbl_step_host (seconds since entry): enqueue done, chunks published, finished."""
+    buf = (C.c_double * 66)()
+    k = LIB.gbl_host_last_timing(buf, 66)
+    return [buf[i] for i in range(min(k, 66))]
 
 
 def host_threads(threads: int = 0) -> int:

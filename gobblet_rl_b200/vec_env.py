@@ -258,11 +258,15 @@ class HostVecEnv:
         self.device = torch.device(device)
         self.num_envs = n = int(num_envs)
         self.wire, self.expand, self.host_threads = wire, bool(expand), int(host_threads)
-        if chunks is None:
-            chunks = 8 if wire == "packed" else 2
         # chunk boundaries on multiples of 1024 envs (the expander's work item: every chunk starts 64-byte aligned)
-        chunks = max(1, min(int(chunks), n // 1024))
-        bounds = [min(n, -(-n * i // chunks // 1024) * 1024) for i in range(chunks)] + [n]
+        if chunks is None and wire == "packed":
+            # small first chunks (the host cores start expanding a few microseconds after the kernel), large later
+            # ones (few API calls): 1/64, 1/32, 1/16, 1/8, 1/4, 1/2, 3/4, 1 of the envs
+            fr = (1 / 64, 1 / 32, 1 / 16, 1 / 8, 1 / 4, 1 / 2, 3 / 4)
+            bounds = sorted({0, *(min(n, -(-int(n * f) // 1024) * 1024) for f in fr)} - {n}) + [n]
+        else:
+            chunks = max(1, min(int(2 if chunks is None else chunks), n // 1024))
+            bounds = [min(n, -(-n * i // chunks // 1024) * 1024) for i in range(chunks)] + [n]
         self.parts = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
         self.env = VecEnv(n, device=device, **kw)
         self.envs = [self.env]

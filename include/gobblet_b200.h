@@ -168,6 +168,9 @@ GBL_API int gbl_step_host(void *state, const uint8_t *actions_host, int64_t n, u
  * mode: 0 = non-temporal stores, 1 = regular stores. */
 GBL_API int gbl_host_fill(void *dst, int64_t bytes, int32_t nthreads, int32_t mode);
 GBL_API int gbl_host_threads(int32_t nthreads);
+/* wall-clock marks (seconds since entry) of this thread's last gbl_step_host call: [0] everything enqueued,
+ * [1 .. nchunks] chunk c handed to the expander, [nchunks + 1] expansion finished; returns how many there are */
+GBL_API int gbl_host_last_timing(double *out, int32_t cap);
 GBL_API int gbl_host_simd(void);
 /* GBL_HOST_STORE_MODE: gbl_host_set_store_mode(0) = staged + non-temporal (default), 1 = direct regular stores */
 GBL_API int gbl_host_set_store_mode(int32_t mode);

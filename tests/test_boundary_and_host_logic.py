@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     from gobblet_rl_b200 import ops
     header = open(os.path.join(REPO, "include", "gobblet_b200.h")).read()
     declared = sorted(set(re.findall(r"GBL_API\s+(?:const\s+)?\w+\s*\*?\s*(gbl_\w+)\s*\(", header)))
-    assert len(declared) == 20 and set(declared) == set(ops.EXPORTED_SYMBOLS)
+    assert len(declared) == 21 and set(declared) == set(ops.EXPORTED_SYMBOLS)
     lib = C.CDLL(ops.LIB_PATH)
     for name in declared:
         assert getattr(lib, name) is not None
