@@ -22,12 +22,16 @@
 //  * A block works through several boards per warp, so the line table is staged once per block.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/gobblet_b200.h"
 #include "gobblet_core.cuh"
 
 namespace gbl {
 
+#ifndef GBL_GREEDY_MIN_BLOCKS
+#define GBL_GREEDY_MIN_BLOCKS 5     // resident blocks per SM asked of the compiler (48 registers; 4 / 5 / 6 measured: 123 / 120 / 149 us)
+#endif
 constexpr int GREEDY_BLOCK = 256, GREEDY_WARPS = GREEDY_BLOCK / 32;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
@@ -73,16 +77,25 @@ __device__ __forceinline__ void tops_after(uint32_t t_mover, uint32_t u_mover, u
     other = (t_other | (u_other & o)) & ~p;
 }
 
-__global__ void __launch_bounds__(GREEDY_BLOCK)
+__global__ void __launch_bounds__(GREEDY_BLOCK, GBL_GREEDY_MIN_BLOCKS)
 greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, const int16_t *__restrict__ prev3,
               int32_t depth, uint64_t seed, uint64_t ctr_base, int32_t *act, int32_t *chosen_out,
               uint64_t *cand_out, uint8_t *fallback_out, int64_t n, int32_t boards_per_warp) {
-    __shared__ __align__(16) uint8_t lut[512];
-    __shared__ uint4 rootinfo[GREEDY_WARPS][56];
+    // the table is 512-byte aligned: a 9-bit index is OR-ed into its shared-memory address, and that OR folds into
+    // the LOP3 that produces the index (no address add per look-up)
+    __shared__ __align__(512) uint8_t lut[512];
+    __shared__ __align__(16) uint32_t rootinfo[GREEDY_WARPS][56][8];
     reinterpret_cast<uint16_t *>(lut)[threadIdx.x] = reinterpret_cast<const uint16_t *>(kLineLut.v)[threadIdx.x];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *const info = rootinfo[warp];
+    uint32_t (*const info)[8] = rootinfo[warp];
+    uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));            // opaque: keeps the compiler from re-deriving the address in the root loop
+    auto lines = [lut_s](uint32_t tops9) -> uint32_t {        // complete-line set of a 9-bit top map: one LDS.U8
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s | tops9));
+        return v;
+    };
 
     // ---- per-lane constants: the actions this lane evaluates in round 0 / 1 (a = lane, lane + 32) ----------
     uint32_t pbit[2], fsh[2], is_y[2];
@@ -148,7 +161,7 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
             org_op[r] = ((is_y[r] ? yp : xp) >> fsh[r]) & 0x1FFu;            // same for the opponent's piece (replies)
             tops_after(t0.tm, t0.um, t0.to, t0.uo, org_me[r], pbit[r], tm1[r], to1[r]);
             const bool cand_here = (keys >> (lane + 32u * r)) & 1ull;
-            const uint32_t lm = lut[tm1[r]], lt = lut[to1[r]];
+            const uint32_t lm = lines(tm1[r]), lt = lines(to1[r]);
             win[r] = cand_here && lm > lt;
             loss[r] = cand_here && lt > lm;
         }
@@ -179,7 +192,8 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
                     uint32_t rl, rh;
                     legal_mask(xp, yp, u1, u1 >> 9, rl, rh);
                     const Tops t1 = summarize(x1 | y1, xp | yp);
-                    info[a] = make_uint4(rl, rh | (t1.tm << 22), t1.to | (t1.um << 9) | (t1.uo << 18), 0u);
+                    *reinterpret_cast<uint4 *>(info[a]) = make_uint4(rl, rh, t1.tm, t1.to);     // every fact in its own word:
+                    *reinterpret_cast<uint2 *>(info[a] + 4) = make_uint2(t1.um, t1.uo);         // no unpacking in the root loop
                 }
             }
             __syncwarp();
@@ -191,15 +205,16 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
             for (int half = 0; half < 2 && !done; ++half) {                  // 32-bit root sets: cheaper loop control than 64-bit
                 for (uint32_t rs = half ? (uint32_t)(roots >> 32) : (uint32_t)roots; rs; rs &= rs - 1u) {
                     const int a = 32 * half + __ffs((int)rs) - 1;
-                    const uint4 ri = info[a];                                // one broadcast LDS.128
-                    const uint32_t rtm = ri.y >> 22, rto = ri.z & 0x1FFu, rum = (ri.z >> 9) & 0x1FFu, ruo = ri.z >> 18;
-                    const uint32_t rep[2] = {ri.x, ri.y & 0x003FFFFFu};
+                    const uint4 ri = *reinterpret_cast<const uint4 *>(info[a]);          // broadcast LDS.128 + LDS.64
+                    const uint2 rj = *reinterpret_cast<const uint2 *>(info[a] + 4);
+                    const uint32_t rtm = ri.z, rto = ri.w, rum = rj.x, ruo = rj.y;
+                    const uint32_t rep[2] = {ri.x, ri.y};
                     bool opp_wins = false, not_mine = false;
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         uint32_t tt, tm;
                         tops_after(rto, ruo, rtm, rum, org_op[r], pbit[r], tt, tm);  // the opponent is the mover
-                        const uint32_t lt = lut[tt], lm = lut[tm];
+                        const uint32_t lt = lines(tt), lm = lines(tm);
                         const bool is_reply = (rep[r] >> lane) & 1u;
                         opp_wins = __any_sync(FULL, is_reply && lt > lm);
                         if (opp_wins) break;                                 // unsafe root: nothing else matters here
@@ -221,15 +236,16 @@ greedy_kernel(const int8_t *__restrict__ obs, const int8_t *__restrict__ mask, c
                 int nc = ncand_d1;
                 for (uint64_t rs = unsafe; rs && nc > 1; rs &= rs - 1) {
                     const int a = __ffsll((long long)rs) - 1;
-                    const uint4 ri = info[a];
-                    const uint32_t rtm = ri.y >> 22, rto = ri.z & 0x1FFu, rum = (ri.z >> 9) & 0x1FFu, ruo = ri.z >> 18;
-                    const uint32_t rep[2] = {ri.x, ri.y & 0x003FFFFFu};
+                    const uint4 ri = *reinterpret_cast<const uint4 *>(info[a]);
+                    const uint2 rj = *reinterpret_cast<const uint2 *>(info[a] + 4);
+                    const uint32_t rtm = ri.z, rto = ri.w, rum = rj.x, ruo = rj.y;
+                    const uint32_t rep[2] = {ri.x, ri.y};
                     uint32_t theirs[2];
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         uint32_t tt, tm;
                         tops_after(rto, ruo, rtm, rum, org_op[r], pbit[r], tt, tm);
-                        theirs[r] = __ballot_sync(FULL, ((rep[r] >> lane) & 1u) && lut[tt] > lut[tm]);
+                        theirs[r] = __ballot_sync(FULL, ((rep[r] >> lane) & 1u) && lines(tt) > lines(tm));
                     }
                     const uint64_t W = (uint64_t)theirs[0] | ((uint64_t)theirs[1] << 32);
                     --nc;                                                    // this root left the candidate list
@@ -273,11 +289,13 @@ extern "C" int gbl_greedy(const int8_t *obs, const int8_t *mask, const int16_t *
     if (n < 0 || depth < 1 || depth > 2) { gbl__set_error("gbl_greedy: n < 0 or depth not in {1,2}"); return GBL_E_INVALID; }
     if (n == 0) return 0;
     if (!obs || !mask || !act) { gbl__set_error("gbl_greedy: obs/mask/act must be non-null"); return GBL_E_INVALID; }
-    // several boards per warp once the grid fills the machine (the block stages the line table once);
-    // a chunk of boards per block keeps the hardware block scheduler as the load balancer
-    const int64_t warps_full = 148 * 4 * gbl::GREEDY_WARPS * 2;
-    int32_t bpw = (int32_t)(n / warps_full);
-    bpw = bpw < 1 ? 1 : bpw > 8 ? 8 : bpw;
+    // a few boards per warp once the grid fills the machine (the block stages the line table once per 8 * bpw boards),
+    // but still several waves of blocks so that the hardware block scheduler evens out the uneven boards
+    // (65 536 boards: 1 / 2 / 3 / 4 / 6 / 8 boards per warp measured 121 / 117 / 117 / 118 / 119 / 125 us)
+    const int64_t warps_4_waves = 148 * GBL_GREEDY_MIN_BLOCKS * gbl::GREEDY_WARPS * 4;
+    int32_t bpw = (int32_t)(n / warps_4_waves);
+    bpw = bpw < 1 ? 1 : bpw > 4 ? 4 : bpw;
+    if (const char *env = getenv("GBL_GREEDY_BPW")) bpw = atoi(env) > 0 ? atoi(env) : bpw;       // tuning knob
     const int64_t per_block = (int64_t)gbl::GREEDY_WARPS * bpw;
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     gbl::greedy_kernel<<<grid, gbl::GREEDY_BLOCK, 0, (cudaStream_t)stream>>>(obs, mask, prev3, depth, seed, ctr_base, act,
