@@ -262,7 +262,7 @@ __device__ __forceinline__ uint32_t sample_action(uint32_t m0, uint32_t m1, uint
 //     (nibble * 0x00204081 & 0x01010101).
 // Per warp and step: one 3744-byte bulk store + 108 full 128-bit, fully coalesced STG for the mask
 // (234 + 108 STG with -DGBL_BULK_STORE=0 and in the ragged last warp).
-// Protocol: stage_env | __syncwarp | emit_chunk | __syncwarp, repeated; see the comments of both.
+// Protocol: [stage_recycle] | stage_env | __syncwarp | emit_chunk | __syncwarp, repeated; see the comments of each.
 constexpr int OBS_IMG_BYTES = 32 * 117, MASK_WORDS = 54;
 constexpr int STAGE_BYTES = OBS_IMG_BYTES + 4 * MASK_WORDS + 8;  // 3968, multiple of 16
 constexpr int OBS_VEC = 234, MASK_VEC = 108;                    // uint4 stores per warp
@@ -361,6 +361,24 @@ __device__ __forceinline__ void fence_smem_for_bulk() {    // generic-proxy smem
 #endif
 }
 
+// Bulk path only: take the observation image back from the copy engine (the bulk store issued by the previous
+// emit_chunk must have READ it) and zero it for the next scatter.  Callers put it right before stage_env, i.e.
+// AFTER the register-only game logic of the next step: the engine reads the 3744 bytes while the warp computes
+// (waiting right behind the mask stores -- the first version -- cost a third of all warp stall samples).
+template <bool kBulk = kBulkStore>
+__device__ __forceinline__ void stage_recycle(uint8_t *stage, uint32_t lane) {
+    if (!kBulk) return;
+    if (lane == 0) bulk_store_wait_read();
+    __syncwarp();
+    uint4 *img = reinterpret_cast<uint4 *>(stage);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t q = lane + 32u * i;
+        if (i < 7 || q < OBS_VEC) img[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+}
+
 // stage: all 32 lanes of the warp must call (shuffle inside).  stage = this warp's STAGE_BYTES.
 // The caller puts a __syncwarp() between stage_env and emit_chunk and one after emit_chunk.
 template <bool kBulk = kBulkStore>
@@ -422,15 +440,7 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
             uint32_t q = lane + 32u * i;
             if ((i < 3 || q < MASK_VEC) && !(skip & 2u)) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
         }
-        if (kBulk) {                           // re-zero the image once the copy engine has read it
-            if (lane == 0) bulk_store_wait_read();
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t q = lane + 32u * i;
-                if (i < 7 || q < OBS_VEC) img[q] = zero;
-            }
-        }
+        // kBulk: the image stays with the copy engine; stage_recycle() takes it back before the next stage_env
     } else {  // ragged last warp: vector stores while fully inside, bytes at the edge
         const uint32_t ob = 117u * nvalid, mb = 54u * nvalid;
         for (uint32_t q = lane; q < OBS_VEC; q += 32u) {

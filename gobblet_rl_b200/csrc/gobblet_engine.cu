@@ -81,7 +81,8 @@ observe_kernel(const ulonglong2 *__restrict__ state, int8_t *obs, int8_t *mask, 
     __syncwarp();
     emit_chunk<kStreaming>(stage[warp], lane, obs + first * GBL_OBS_BYTES, mask + first * GBL_MASK_BYTES, nvalid);
     if (agent_id && valid) agent_id[g] = (uint8_t)e.agent;
-    if (kBulkStore && lane == 0) bulk_store_wait_all();
+    // the block may retire once the copy engine has READ the image (the global writes complete by kernel end)
+    if (kBulkStore && lane == 0) bulk_store_wait_read();
 }
 
 // ---- externally driven step ----------------------------------------------------------------------
@@ -142,11 +143,11 @@ __global__ void __launch_bounds__(BLOCK, GBL_STEP_MIN_BLOCKS) step_kernel(StepPa
             }
         }
         __syncwarp();
+        if (same_step && p.final_obs && p.final_mask) stage_recycle(stage[warp], lane);
         stage_env(stage[warp], cfg, lane, e, m0, m1);
         __syncwarp();
         emit_chunk<kStreaming>(stage[warp], lane, p.obs + first * GBL_OBS_BYTES,
                                p.mask + first * GBL_MASK_BYTES, nvalid);
-        if (kBulkStore && lane == 0) bulk_store_wait_all();
         if (valid) {
             p.state[g] = env_pack(e);
             if (p.rew2) *reinterpret_cast<char2 *>(p.rew2 + 2 * g) = make_char2((signed char)r.r1, (signed char)r.r2);
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(BLOCK, GBL_STEP_MIN_BLOCKS) step_kernel(StepPa
             if (p.truncated) p.truncated[g] = r.trunc;
             if (p.agent_id) p.agent_id[g] = (uint8_t)e.agent;
         }
+        if (kBulkStore && lane == 0) bulk_store_wait_read();   // shared memory may go once the engine has read the image
     }
     if (p.stats) flush_stats(st, valid, p.stats);
 }
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
         const uint32_t initial = kAux && (p.flags & GBL_EMIT_INITIAL) ? 1u : 0u;
         if (initial) {                          // trajectory-buffer layout: slot 0 = the observation before the first step
             if (emit) {
+                stage_recycle<kBulk && kBulkStore>(stage, lane);
                 stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
                 emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + first * GBL_OBS_BYTES, p.mask_out + first * GBL_MASK_BYTES, nvalid, opts);
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
             occupancy(e, u, up);
             legal_mask(e.xo, e.yo, u, up, m0, m1);
             if (kAux && p.final_obs_out) {      // the observation a same-step reset is about to replace
+                stage_recycle<kBulk && kBulkStore>(stage, lane);
                 stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
                 emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.final_obs_out + (int64_t)(slot - initial) * p.obs_slot_stride + first * GBL_OBS_BYTES,
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                 if (p.action_log) p.action_log[(int64_t)t * p.n + g] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
             if (emit) {
+                stage_recycle<kBulk && kBulkStore>(stage, lane);
                 stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
                 emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
@@ -263,13 +268,13 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
         }
-        if (kBulk && kBulkStore && lane == 0) bulk_store_wait_all();
         if (valid) p.state[g] = env_pack(e);
         if (kFast) {   // every step but a reset-only first one was a live, legal step: these follow from the step count
             st.steps = live_steps;
             st.sumlen = plies_start + live_steps - e.plies;
             st.p2w = st.episodes - st.p1w;
         }
+        if (kBulk && kBulkStore && lane == 0) bulk_store_wait_read();
     }
     if (p.stats) flush_stats<kBlock / 32>(st, valid, p.stats);
 }

@@ -5,6 +5,7 @@ sm_100a kernels behind the C ABI.  There is NO fallback: if the library cannot b
 with nvcc) importing this module raises.
 """
 import ctypes as C
+import functools
 from typing import Optional
 
 import torch
@@ -97,6 +98,25 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _on_device:
+    """Make `dev` the current CUDA device around a launch; costs nothing when it already is (the usual case --
+    torch.cuda.device() pays two cudaSetDevice round trips per call)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.idx is not None and self.idx != self.prev:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.idx is not None and self.idx != self.prev:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _need_cuda(*tensors):
     dev = None
     for t in tensors:
@@ -129,24 +149,43 @@ def _need_state(state: torch.Tensor):
 
 
 # ---- torch custom ops (schema + fake impls so the engine composes with torch.compile / graphs) ------
-@torch.library.custom_op("gobblet_b200::reset", mutates_args=("state",))
+def _engine_op(name: str, mutates):
+    """Register `fn` as the torch custom op gobblet_b200::<name> (schema with mutated arguments + a fake impl, so a
+    caller's step function composes with torch.compile) and return a thin dispatcher: under tracing the custom op
+    is recorded, in eager mode the function is called DIRECTLY -- the custom-op dispatcher costs tens of
+    microseconds per call, as long as the kernels themselves."""
+    def deco(fn):
+        op = torch.library.custom_op(f"gobblet_b200::{name}", mutates_args=tuple(mutates))(fn)
+        op.register_fake(lambda *a, **k: None)
+
+        @functools.wraps(fn)
+        def call(*a, **k):
+            if torch.compiler.is_compiling():
+                return op(*a, **k)
+            return fn(*a, **k)
+
+        call.op = op
+        return call
+    return deco
+
+@_engine_op("reset", ("state",))
 def reset(state: torch.Tensor, which: Optional[torch.Tensor] = None) -> None:
     dev = _need_cuda(state, which)
     _need_bytes("which", which, _need_state(state))
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_reset_masked(_ptr(state), _ptr(which), state.shape[0], _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::observe", mutates_args=("obs", "mask", "agent_id"))
+@_engine_op("observe", ("obs", "mask", "agent_id"))
 def observe(state: torch.Tensor, obs: torch.Tensor, mask: torch.Tensor, agent_id: Optional[torch.Tensor]) -> None:
     dev = _need_cuda(state, obs, mask, agent_id)
     n = _need_state(state)
     _need_bytes("obs", obs, n * OBS_BYTES); _need_bytes("mask", mask, n * MASK_BYTES); _need_bytes("agent_id", agent_id, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_observe(_ptr(state), _ptr(obs), _ptr(mask), _ptr(agent_id), state.shape[0], _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::step", mutates_args=("state", "obs", "mask", "rew", "terminated", "truncated",
+@_engine_op("step", ("state", "obs", "mask", "rew", "terminated", "truncated",
                                                              "agent_id", "final_obs", "final_mask", "stats"))
 def step(state: torch.Tensor, actions: torch.Tensor, obs: torch.Tensor, mask: torch.Tensor,
          rew: Optional[torch.Tensor], terminated: Optional[torch.Tensor], truncated: Optional[torch.Tensor],
@@ -161,14 +200,13 @@ def step(state: torch.Tensor, actions: torch.Tensor, obs: torch.Tensor, mask: to
                              ("final_mask", final_mask, MASK_BYTES)):
         _need_bytes(name, t, n * per_env)
     _need_bytes("stats", stats, 64, 8)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_step(_ptr(state), _ptr(actions), actions.element_size(), _ptr(obs), _ptr(mask), _ptr(rew),
                             _ptr(terminated), _ptr(truncated), _ptr(agent_id), _ptr(final_obs), _ptr(final_mask),
                             _ptr(stats), state.shape[0], flags, _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::rollout_random",
-                         mutates_args=("state", "obs_out", "mask_out", "rew_out", "term_out", "agent_out",
+@_engine_op("rollout_random", ("state", "obs_out", "mask_out", "rew_out", "term_out", "agent_out",
                                        "action_log", "stats", "final_obs_out", "final_mask_out"))
 def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, step_base: int,
                    obs_out: Optional[torch.Tensor], mask_out: Optional[torch.Tensor],
@@ -214,14 +252,14 @@ def rollout_random(state: torch.Tensor, T: int, seed: int, env_id_base: int, ste
                 or final_mask_out.stride(0) != sm or final_obs_out.element_size() != 1 or final_mask_out.element_size() != 1
                 or not final_obs_out[0].is_contiguous() or not final_mask_out[0].is_contiguous()):
             raise GobbletError("final_obs_out / final_mask_out must match obs_out / mask_out in shape and slot stride")
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_rollout_random(_ptr(state), n, T, seed & (2**64 - 1), env_id_base, step_base, _ptr(step_dev), _ptr(obs_out),
                                       _ptr(mask_out), so, sm, ring, _ptr(rew_out), _ptr(term_out), _ptr(agent_out),
                                       _ptr(action_log), _ptr(final_obs_out), _ptr(final_mask_out), _ptr(stats), flags,
                                       _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::step_packed", mutates_args=("state", "rec", "final_rec", "stats"))
+@_engine_op("step_packed", ("state", "rec", "final_rec", "stats"))
 def step_packed(state: torch.Tensor, actions: torch.Tensor, rec: torch.Tensor, final_rec: Optional[torch.Tensor],
                 stats: Optional[torch.Tensor], flags: int) -> None:
     """gbl_step in the packed wire format: rec int32 [n, 6] (24 bytes per env, include/gobblet_b200.h)."""
@@ -230,32 +268,32 @@ def step_packed(state: torch.Tensor, actions: torch.Tensor, rec: torch.Tensor, f
     if actions.dtype not in (torch.uint8, torch.int32, torch.int64) or actions.numel() != n:
         raise GobbletError("actions must be uint8 / int32 / int64 with one entry per env")
     _need_bytes("rec", rec, 24 * n, 4); _need_bytes("final_rec", final_rec, 24 * n, 4); _need_bytes("stats", stats, 64, 8)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_step_packed(_ptr(state), _ptr(actions), actions.element_size(), _ptr(rec), _ptr(final_rec),
                                    _ptr(stats), n, flags, _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::observe_packed", mutates_args=("rec",))
+@_engine_op("observe_packed", ("rec",))
 def observe_packed(state: torch.Tensor, rec: torch.Tensor) -> None:
     dev = _need_cuda(state, rec)
     n = _need_state(state)
     _need_bytes("rec", rec, 24 * n, 4)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_observe_packed(_ptr(state), _ptr(rec), n, _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::sample_legal", mutates_args=("act",))
+@_engine_op("sample_legal", ("act",))
 def sample_legal(mask: torch.Tensor, seed: int, env_id_base: int, step: int, act: torch.Tensor,
                  step_dev: Optional[torch.Tensor] = None) -> None:
     dev = _need_cuda(mask, act, step_dev)
     _need_bytes("mask", mask, act.numel() * MASK_BYTES); _need_bytes("act", act, 4 * act.numel(), 4)
     _need_bytes("step_dev", step_dev, 8, 8)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_sample_legal(_ptr(mask), seed & (2**64 - 1), env_id_base, step, _ptr(step_dev), _ptr(act),
                                     act.numel(), _stream(mask)))
 
 
-@torch.library.custom_op("gobblet_b200::greedy", mutates_args=("act", "chosen", "cand", "used_fallback"))
+@_engine_op("greedy", ("act", "chosen", "cand", "used_fallback"))
 def greedy(obs: torch.Tensor, mask: torch.Tensor, prev3: Optional[torch.Tensor], depth: int, seed: int,
            ctr_base: int, act: torch.Tensor, chosen: Optional[torch.Tensor], cand: Optional[torch.Tensor],
            used_fallback: Optional[torch.Tensor]) -> None:
@@ -264,21 +302,21 @@ def greedy(obs: torch.Tensor, mask: torch.Tensor, prev3: Optional[torch.Tensor],
     _need_bytes("obs", obs, n * OBS_BYTES); _need_bytes("mask", mask, n * MASK_BYTES); _need_bytes("prev3", prev3, 6 * n, 2)
     _need_bytes("act", act, 4 * n, 4); _need_bytes("chosen", chosen, 4 * n, 4); _need_bytes("cand", cand, 8 * n, 8)
     _need_bytes("used_fallback", used_fallback, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_greedy(_ptr(obs), _ptr(mask), _ptr(prev3), depth, seed & (2**64 - 1), ctr_base, _ptr(act),
                               _ptr(chosen), _ptr(cand), _ptr(used_fallback), act.numel(), _stream(obs)))
 
 
-@torch.library.custom_op("gobblet_b200::export_squares", mutates_args=("squares", "agent"))
+@_engine_op("export_squares", ("squares", "agent"))
 def export_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor]) -> None:
     dev = _need_cuda(state, squares, agent)
     n = _need_state(state)
     _need_bytes("squares", squares, 27 * n); _need_bytes("agent", agent, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_export_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _stream(state)))
 
 
-@torch.library.custom_op("gobblet_b200::import_squares", mutates_args=("state", "invalid_count"))
+@_engine_op("import_squares", ("state", "invalid_count"))
 def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[torch.Tensor],
                    invalid_count: Optional[torch.Tensor]) -> None:
     """invalid_count: optional int32[1] CUDA tensor, incremented per env whose squares the reference would reject
@@ -286,14 +324,11 @@ def import_squares(state: torch.Tensor, squares: torch.Tensor, agent: Optional[t
     dev = _need_cuda(state, squares, agent, invalid_count)
     n = _need_state(state)
     _need_bytes("squares", squares, 27 * n); _need_bytes("agent", agent, n); _need_bytes("invalid_count", invalid_count, 4, 4)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(LIB.gbl_import_squares(_ptr(state), _ptr(squares), _ptr(agent), state.shape[0], _ptr(invalid_count),
                                       _stream(state)))
 
 
-for _op in (reset, observe, step, rollout_random, step_packed, observe_packed, sample_legal, greedy, export_squares,
-            import_squares):
-    _op.register_fake(lambda *a, **k: None)
 
 
 # ---- host side of the packed wire format (plain host memory; no torch custom op: nothing here is traced) ----
@@ -346,7 +381,7 @@ class HostStepPlan:
         if actions_host.is_cuda or actions_host.dtype != torch.uint8 or actions_host.numel() != self.n:
             raise GobbletError("actions must be a host uint8 tensor with one entry per env")
         st, da, dr, hr = self.ptrs
-        with torch.cuda.device(self.device):
+        with _on_device(self.device):
             _check(LIB.gbl_step_host(st, _ptr(actions_host), self.n, self.flags, da, dr, hr, self.k, self.ends, self.stream,
                                      self.events, *self.out, self.stats, self.threads))
 
