@@ -243,9 +243,12 @@ __device__ __forceinline__ uint32_t select_bit(uint32_t m0, uint32_t m1, uint32_
     return pos;
 }
 
-// uniform legal action: j = floor(draw * count / 2^32)
+// uniform legal action: j = floor(draw * count / 2^32).  kNonEmpty: the caller knows the mask has a set bit (every
+// valid position has >= 10 legal actions), so the empty-mask guard -- a divergent region around the search -- goes.
+template <bool kNonEmpty = false>
 __device__ __forceinline__ uint32_t sample_action(uint32_t m0, uint32_t m1, uint32_t draw) {
     uint32_t cnt = __popc(m0) + __popc(m1);
+    if (kNonEmpty) return select_bit(m0, m1, __umulhi(draw, cnt));
     return cnt ? select_bit(m0, m1, __umulhi(draw, cnt)) : 0u;
 }
 
@@ -310,6 +313,17 @@ __device__ __forceinline__ void store_one_if(uint8_t *base, uint32_t off, uint32
                  :: "r"(cond), "r"(addr), "r"(1u) : "memory");
 #else  // host-side emulation used only by tests/emul (never by the product)
     if (cond) base[off] = 1;
+#endif
+}
+
+// store a 32-bit word to shared memory iff cond, as one predicated STS (no divergent region)
+__device__ __forceinline__ void store_word_if(uint32_t *p, uint32_t v, bool cond) {
+#ifdef __CUDA_ARCH__
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}"
+                 :: "r"((uint32_t)cond), "r"(addr), "r"(v) : "memory");
+#else  // host-side emulation used only by tests/emul (never by the product)
+    if (cond) *p = v;
 #endif
 }
 
@@ -389,17 +403,16 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
     scatter_pieces(mine, e.yo, 1);
     scatter_pieces(mine, e.xp, 6);
     scatter_pieces(mine, e.yp, 7);
-    if (e.agent) {                                      // plane 12: the viewer is player_2 (gobblet.py:199-206)
 #pragma unroll
-        for (int p = 0; p < 9; ++p) mine[13 * p + 12] = 1;
-    }
+    for (int p = 0; p < 9; ++p) mine[13 * p + 12] = (uint8_t)e.agent;   // plane 12: the viewer is player_2 (gobblet.py:199-206);
+                                                                         // unconditional (the image is zero): no divergent region
     uint32_t *mbits = reinterpret_cast<uint32_t *>(stage + OBS_IMG_BYTES);
     const uint32_t v0 = m0 << c.mso, v1 = __funnelshift_l(m0, m1, c.mso), v2 = __funnelshift_l(m1, 0u, c.mso);
     uint32_t tail = c.mn2 ? v2 : v1;                    // partial word shared with the next lane
     uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
     if (lane == 0) prev = 0;
     mbits[c.mfo] = v0 | prev;
-    if (c.mn2) mbits[c.mfo + 1] = v1;
+    store_word_if(mbits + c.mfo + 1, v1, c.mn2);
     if (kBulk) fence_smem_for_bulk();
 }
 

@@ -7,6 +7,8 @@
 #include <string.h>
 #include <time.h>
 
+#include <type_traits>
+
 #include "../../include/gobblet_b200.h"
 #include "gobblet_core.cuh"
 
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
         env_clear(e);
         if (valid) env_unpack(e, p.state[g]);
         uint32_t plies_start = e.plies, live_steps = (uint32_t)p.T;
-        bool dead0 = kFast && e.done;
+        const bool dead0 = kFast && e.done;
         uint32_t u, up, m0, m1;
         occupancy(e, u, up);
         legal_mask(e.xo, e.yo, u, up, m0, m1);
@@ -224,17 +226,29 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
             if (valid && p.agent_out) p.agent_out[g] = (uint8_t)e.agent;
             slot = 1u;
         }
-#pragma unroll 2
-        for (int32_t t = 0; t < p.T; ++t) {     // two plies per trip: the own/opponent register swap becomes renaming
+        // One lockstep step.  kFirst (t == 0, peeled): the Philox block is always drawn, and only here can a fast-path env
+        // be one that ARRIVED finished -- the steady-state body carries neither test.  The body avoids divergent
+        // regions (selects and predicated stores instead of branches) so that the emission of one step and the
+        // register-only game logic around it are scheduled together.
+        auto body = [&](const int32_t t, auto first_tag) {
+            constexpr bool kFirst = decltype(first_tag)::value;
             const uint64_t s = step_base + (uint64_t)t;
-            if (t == 0 || (s & 3u) == 0) rnd = draw_block(p.seed, p.env_id_base + (uint64_t)g, s, 0u);
+            if (kFirst) {
+                rnd = draw_block(p.seed, p.env_id_base + (uint64_t)g, s, 0u);
+                for (uint32_t k = 0; k < ((uint32_t)s & 3u); ++k) rnd = make_uint4(rnd.y, rnd.z, rnd.w, rnd.x);
+            } else if ((s & 3u) == 0) {
+                rnd = draw_block(p.seed, p.env_id_base + (uint64_t)g, s, 0u);
+            }
+            const uint32_t draw = rnd.x;        // word (s & 3) of the block: the vector is rotated one word per step
+            rnd = make_uint4(rnd.y, rnd.z, rnd.w, rnd.x);
             uint32_t action = 255u;
             StepResult r;
-            if (kFast && dead0) {               // reset-only step of an env that arrived finished
+            if (kFirst && kFast && dead0) {     // reset-only step of an env that arrived finished
                 r = {0, 0, true, e.trunc != 0, false, false};
-                dead0 = false; plies_start = 0; --live_steps;
+                plies_start = 0; --live_steps;
             } else {
-                if (kFast || !e.done) action = sample_action(m0, m1, pick_word(rnd, (uint32_t)s & 3u));
+                if (kFast) action = sample_action<true>(m0, m1, draw);
+                else if (!e.done) action = sample_action(m0, m1, draw);
                 r = env_step<kFast>(e, m0, m1, action, p.flags, st);
             }
             occupancy(e, u, up);
@@ -247,9 +261,11 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                                        p.final_mask_out + (int64_t)(slot - initial) * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
-            if (r.term && same_step) {          // raw_env.reset: empty board, player_1 to move, every action legal
-                env_clear(e);
-                m0 = 0xFFFFFFFFu; m1 = 0x003FFFFFu;
+            {                                   // raw_env.reset (same-step): empty board, player_1 to move, every action legal
+                const bool rs = r.term && same_step;
+                e.xo = rs ? 0u : e.xo; e.yo = rs ? 0u : e.yo; e.xp = rs ? 0u : e.xp; e.yp = rs ? 0u : e.yp;
+                e.agent = rs ? 0u : e.agent; e.plies = rs ? 0u : e.plies; e.done = rs ? 0u : e.done; e.trunc = rs ? 0u : e.trunc;
+                m0 = rs ? 0xFFFFFFFFu : m0; m1 = rs ? 0x003FFFFFu : m1;
             }
             if (kAux && valid) {
                 const int64_t o = (int64_t)slot * p.n + g, oa = o - (int64_t)initial * p.n;   // [T+1] slots vs [T] slots
@@ -267,7 +283,10 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                 __syncwarp();
             }
             slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
-        }
+        };
+        body(0, std::true_type{});
+#pragma unroll 2
+        for (int32_t t = 1; t < p.T; ++t) body(t, std::false_type{});   // two plies per trip: the own/opponent register swap becomes renaming
         if (valid) p.state[g] = env_pack(e);
         if (kFast) {   // every step but a reset-only first one was a live, legal step: these follow from the step count
             st.steps = live_steps;
