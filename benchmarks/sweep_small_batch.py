@@ -17,8 +17,8 @@ from gobblet_rl_b200 import gobblet_v1  # noqa: E402
 def main():
     dev = torch.device("cuda", 0)
     out = {}
-    for n in (1024, 4096, 16384, 65536):
-        T = 4096 if n <= 16384 else 512
+    for n in (1024, 4096, 16384, 32768, 65536, 131072, 262144):
+        T = 4096 if n <= 16384 else 512 if n <= 65536 else 128
         vec = gobblet_v1.vec_env(n, device=dev, seed=0)
         res = {}
         for hint in (0, 32, 64, 128, 256):

@@ -187,7 +187,7 @@ struct RolloutParams {
 // kBulk: the observation image leaves through the copy engine (TMA bulk store); false = 32-lane LDS.128 -> STG.128 copy,
 //        which has no asynchronous completion to wait for (small batches: one warp per scheduler, latency-bound)
 template <bool kFast, bool kStreaming, bool kAux, int kBlock, bool kBulk>
-__global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutParams p) {
+__global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rollout_kernel(RolloutParams p) {
     extern __shared__ __align__(16) uint8_t stage_all[];      // (kBlock/32) * STAGE_BYTES, one staging area per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x, first = g - lane;
@@ -226,6 +226,13 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
             if (valid && p.agent_out) p.agent_out[g] = (uint8_t)e.agent;
             slot = 1u;
         }
+        // byte offsets of this warp's chunk / this lane's element in the current slot, advanced by one slot per step
+        // (a 64-bit add each instead of a 64-bit multiply-add per store address)
+        int64_t obs_off = (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES;
+        int64_t mask_off = (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES;
+        int64_t aux_off = (int64_t)slot * p.n + g, log_off = g;
+        const int64_t fin_obs_shift = (int64_t)initial * p.obs_slot_stride, fin_mask_shift = (int64_t)initial * p.mask_slot_stride;
+        const int64_t aux_shift = (int64_t)initial * p.n;                     // [T+1] observation / agent slots vs [T] reward / flag slots
         // One lockstep step.  kFirst (t == 0, peeled): the Philox block is always drawn, and only here can a fast-path env
         // be one that ARRIVED finished -- the steady-state body carries neither test.  The body avoids divergent
         // regions (selects and predicated stores instead of branches) so that the emission of one step and the
@@ -257,8 +264,8 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                 stage_recycle<kBulk && kBulkStore>(stage, lane);
                 stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.final_obs_out + (int64_t)(slot - initial) * p.obs_slot_stride + first * GBL_OBS_BYTES,
-                                       p.final_mask_out + (int64_t)(slot - initial) * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
+                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.final_obs_out + (obs_off - fin_obs_shift),
+                                       p.final_mask_out + (mask_off - fin_mask_shift), nvalid, opts);
                 __syncwarp();
             }
             {                                   // raw_env.reset (same-step): empty board, player_1 to move, every action legal
@@ -268,21 +275,27 @@ __global__ void __launch_bounds__(kBlock, 1024 / kBlock) rollout_kernel(RolloutP
                 m0 = rs ? 0xFFFFFFFFu : m0; m1 = rs ? 0x003FFFFFu : m1;
             }
             if (kAux && valid) {
-                const int64_t o = (int64_t)slot * p.n + g, oa = o - (int64_t)initial * p.n;   // [T+1] slots vs [T] slots
+                const int64_t oa = aux_off - aux_shift;
                 if (p.rew_out) *reinterpret_cast<char2 *>(p.rew_out + 2 * oa) = make_char2((signed char)r.r1, (signed char)r.r2);
                 if (p.term_out) p.term_out[oa] = r.term;
-                if (p.agent_out) p.agent_out[o] = (uint8_t)e.agent;
-                if (p.action_log) p.action_log[(int64_t)t * p.n + g] = r.acted ? (uint8_t)action : (uint8_t)255;
+                if (p.agent_out) p.agent_out[aux_off] = (uint8_t)e.agent;
+                if (p.action_log) p.action_log[log_off] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
             if (emit) {
                 stage_recycle<kBulk && kBulkStore>(stage, lane);
                 stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + (int64_t)slot * p.obs_slot_stride + first * GBL_OBS_BYTES,
-                                       p.mask_out + (int64_t)slot * p.mask_slot_stride + first * GBL_MASK_BYTES, nvalid, opts);
+                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + obs_off, p.mask_out + mask_off, nvalid, opts);
                 __syncwarp();
             }
-            slot = slot + 1u == (uint32_t)p.ring ? 0u : slot + 1u;
+            log_off += p.n;
+            if (slot + 1u == (uint32_t)p.ring) {     // uniform, and rare in a trajectory (ring >= T): back to slot 0
+                slot = 0u;
+                obs_off = first * GBL_OBS_BYTES; mask_off = first * GBL_MASK_BYTES; aux_off = g;
+            } else {
+                ++slot;
+                obs_off += p.obs_slot_stride; mask_off += p.mask_slot_stride; aux_off += p.n;
+            }
         };
         body(0, std::true_type{});
 #pragma unroll 2
@@ -502,7 +515,7 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) /
 // so that every SM (x 4 schedulers) gets warps and the hardware spreads them evenly (BASELINE config 2, 4096
 // envs, is latency-bound: ~1500 cycles of dependent instructions per warp-step).  Measured on a B200
 // (benchmarks/sweep_small_batch.py, profiles/r2_sweep_small_batch.json): 32-thread blocks are fastest up to 64 Ki
-// envs; below ~5 Ki envs copying the observation image with the lanes beats the copy engine by 3 %.
+// envs; below ~24 Ki envs copying the observation image with the lanes beats the copy engine (8 % at 16 Ki).
 static int rollout_block_for(int64_t n, uint32_t flags) {
     const uint32_t hint = (flags >> GBL_BLOCK_HINT_SHIFT) & 7u;
     if (hint) return hint == 1 ? 32 : hint == 2 ? 64 : hint == 3 ? 128 : 256;
@@ -619,8 +632,9 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     const bool plain = flags & GBL_STORE_DEFAULT_POLICY;
     cudaStream_t s = (cudaStream_t)stream;
     const int block = rollout_block_for(n, flags);
-    // lane copy instead of the copy engine: on request, or by default when there is at most one warp per SM
-    const bool bulk = !((flags & GBL_NO_BULK_STORE_HINT) || (!((flags >> GBL_BLOCK_HINT_SHIFT) & 7u) && n <= 148 * 32));
+    // lane copy instead of the copy engine: on request, or by default up to five warps per SM (latency-bound regime:
+    // 0.65 vs 0.71 us per lockstep step at 16 Ki envs, equal at 32 Ki; profiles/r2_sweep_small_batch.json)
+    const bool bulk = !((flags & GBL_NO_BULK_STORE_HINT) || (!((flags >> GBL_BLOCK_HINT_SHIFT) & 7u) && n <= 148 * 32 * 5));
     const bool aux = rew_out || term_out || agent_out || action_log || final_obs_out || (flags & GBL_EMIT_INITIAL);
 #define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
     do {                                                                            \
