@@ -640,7 +640,7 @@ def main():
             traffic = tj["dram_bytes_per_env_step"] * n * T   # ncu --set full capture scaled to this launch
             traffic_src = "profiles/traffic.json (static ncu --set full capture of this kernel, not measured in this run)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "gbl::rollout_kernel<true,true,false,256>",
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "gbl::rollout_kernel<fast=true, streaming=true, aux=false, block=256, bulk=true>",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
                 "launch_ms_avg": launch_ms, "launch_ms_min": per_launch[0], "launch_ms_median": per_launch[len(per_launch) // 2],
                 "same_run_fill_gbs": fill_gbs, "frac_of_same_run_fill": achieved / fill_gbs,
