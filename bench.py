@@ -570,7 +570,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks
     elapsed_ms = t.item()
-    gpu_launches = vec.kernel_launches - launches0
+    gpu_launches = world * (vec.kernel_launches - launches0)      # whole job: every rank launches the same kernels
     load_windows = [(t_wall0, t_wall1)]
     total_env_steps = world * n * T * a.steps
     value = total_env_steps / (elapsed_ms * 1e-3)
@@ -703,7 +703,7 @@ def main():
                        "l2": f"each launch writes a {ring * n * BYTES_PER_ENV_STEP / 1e9:.1f} GB trajectory once (>> 126 MB L2, no flush needed)",
                        "parallelism": f"{world} independent shards by global env id, no per-step communication",
                        "stores": "st.global" if a.plain_stores else "st.global.cs"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "gpu_launches_per_rank": gpu_launches // world, "clocks": clocks,
             "sustained": sustained, "configs": configs, "multi_gpu_equality": multi_eq,
             "small_batch": None if not configs or "c2" not in configs else
             {"workload": configs["c2"]["workload"], "value": configs["c2"]["value"], "unit": UNIT},
