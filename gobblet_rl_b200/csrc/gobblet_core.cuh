@@ -341,6 +341,9 @@ __device__ __forceinline__ void scatter_pieces(uint8_t *mine, uint32_t w, int pl
 #ifndef GBL_BULK_STORE
 #define GBL_BULK_STORE 1
 #endif
+#ifndef GBL_BULK_EVICT_FIRST
+#define GBL_BULK_EVICT_FIRST 0       // L2 evict-first hint on the bulk store: measured equal (4.034e10 vs 4.034e10 env-steps/s)
+#endif
 #if defined(__CUDA_ARCH__) && GBL_BULK_STORE
 constexpr bool kBulkStore = true;
 #else
@@ -350,7 +353,13 @@ constexpr bool kBulkStore = false;
 __device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, uint32_t bytes) {
 #ifdef __CUDA_ARCH__
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+#if GBL_BULK_EVICT_FIRST
+    uint64_t pol;                        // write-once output: ask L2 to evict these lines first
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" :: "l"(gdst), "r"(saddr), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+#endif
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 #endif
 }
