@@ -43,3 +43,25 @@ def test_two_gpus_equal_one_gpu(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "OK" in res.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_one_process_two_devices_launches_on_the_tensor_device():
+    """Every op makes the device of its tensors current around the launch (`ops._on_device`) and puts it back: an env on
+    cuda:1 driven from a process whose current device is cuda:0 plays the same games as one on cuda:0."""
+    from gobblet_rl_b200 import gobblet_v1
+    assert torch.cuda.current_device() == 0
+    a = gobblet_v1.vec_env(5000, device="cuda:0", seed=21)
+    b = gobblet_v1.vec_env(5000, device="cuda:1", seed=21)
+    oa = a.rollout_random(20, ring=20, per_step=True, log_actions=True)
+    ob = b.rollout_random(20, ring=20, per_step=True, log_actions=True)
+    assert torch.cuda.current_device() == 0
+    for k in oa:
+        assert torch.equal(oa[k].cpu(), ob[k].cpu()), k
+    acts = oa["mask"][-1].to(torch.float32).argmax(1)
+    ra, rb = a.step(acts), b.step(acts.to("cuda:1"))
+    assert all(torch.equal(x.cpu(), y.cpu()) for x, y in zip(ra, rb))
+    ga = gobblet_v1.greedy_actions(ra[0], ra[1], None, depth=2)
+    gb = gobblet_v1.greedy_actions(rb[0], rb[1], None, depth=2)
+    assert torch.equal(ga.cpu(), gb.cpu()) and torch.cuda.current_device() == 0
+    assert a.stats.tolist() == b.stats.tolist()
