@@ -10,6 +10,7 @@ import torch
 
 from . import ops
 
+_ACTION_BYTES = {torch.uint8: 1, torch.int32: 4, torch.int64: 8}
 STAT_NAMES = ("episodes", "player_1_wins", "player_2_wins", "steps", "sum_episode_length", "illegal_moves",
               "both_line_endings", "max_episode_length")
 
@@ -53,6 +54,7 @@ class VecEnv:
         # every rollout, so `rollout_random` can be captured in a CUDA graph and replayed (small-N regime)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev) if graph_safe else None
         self.kernel_launches = 0
+        self._plan = None            # data pointers of the persistent buffers (filled on the first plain step)
         self.reset()
 
     # -- reference surface, batched ------------------------------------------------------------------
@@ -84,6 +86,22 @@ class VecEnv:
         e.g. straight into the slot of a trajectory / replay buffer (no copy).
         With `illegal_mode="terminate"` the observation after an illegal move is the MOVER's (live mask);
         PettingZoo's `last()` would select player_1 there -- `adapters.PettingZooVecEnv` applies that rule."""
+        if (final is None and out is None and aux_out is None and type(actions) is torch.Tensor
+                and actions.dtype in _ACTION_BYTES and actions.device == self.state.device and actions.is_contiguous()
+                and actions.numel() == self.num_envs and not torch.compiler.is_compiling()):
+            # the common call (own buffers, a well-formed CUDA action tensor): pre-marshalled pointers, ONE ctypes call
+            # -- at a few thousand envs the Python side of a step costs more than the kernel
+            plan = self._plan
+            if plan is None:
+                plan = self._plan = tuple(t.data_ptr() for t in (self.state, self.obs, self.mask, self.rew, self.terminated,
+                                                                 self.truncated, self.agent_id, self.stats))
+            st, ob, mk, rw, te, tr, ag, ss = plan
+            dev = self.state.device
+            with ops._on_device(dev):
+                ops._check(ops.LIB.gbl_step(st, actions.data_ptr(), _ACTION_BYTES[actions.dtype], ob, mk, rw, te, tr, ag, None, None,
+                                            ss, self.num_envs, self.flags, torch.cuda.current_stream(dev).cuda_stream))
+            self._advance(1)
+            return self.obs, self.mask, self.rew, self.terminated, self.truncated, self.agent_id
         actions = torch.as_tensor(actions, device=self.device)
         if actions.dtype not in (torch.uint8, torch.int32, torch.int64):
             actions = actions.to(torch.int64)
