@@ -1,4 +1,4 @@
-// gobblet_greedy.cu -- warp-per-board GreedyGobbletPolicy (depth 1 / 2), sm_100a.
+// gobblet_greedy.cu -- warp-per-board GreedyGobbletPolicy (depth 1 / 2; depth 3 == depth 2, see gbl_greedy), sm_100a.
 //
 // Follows gobblet_rl/game/greedy_policy.py:38-221.  The 54 candidate moves (depth 1) and, per surviving root
 // move, the 54 opponent replies (depth 2) are evaluated one per lane in two rounds of 32; warp votes turn the
@@ -286,7 +286,8 @@ extern "C" int gbl__set_error(const char *msg);  // gobblet_engine.cu (thread-lo
 extern "C" int gbl_greedy(const int8_t *obs, const int8_t *mask, const int16_t *prev3, int32_t depth, uint64_t seed,
                           uint64_t ctr_base, int32_t *act, int32_t *chosen, uint64_t *cand, uint8_t *used_fallback,
                           int64_t n, void *stream) {
-    if (n < 0 || depth < 1 || depth > 2) { gbl__set_error("gbl_greedy: n < 0 or depth not in {1,2}"); return GBL_E_INVALID; }
+    if (n < 0 || depth < 1 || depth > 3) { gbl__set_error("gbl_greedy: n < 0 or depth not in {1,2,3}"); return GBL_E_INVALID; }
+    if (depth == 3) depth = 2;      // greedy_policy.py:160-208 cannot change the result of depth 2 (include/gobblet_b200.h)
     if (n == 0) return 0;
     if (!obs || !mask || !act) { gbl__set_error("gbl_greedy: obs/mask/act must be non-null"); return GBL_E_INVALID; }
     // a few boards per warp once the grid fills the machine (the block stages the line table once per 8 * bpw boards),

@@ -37,10 +37,13 @@ def greedy_actions(obs: torch.Tensor, mask: torch.Tensor, prev3: Optional[torch.
 
 class GreedyGobbletPolicy:
     def __init__(self, depth: Optional[int] = 2, seed: Optional[int] = 0, device="cuda", **kwargs: Any) -> None:
-        if depth not in (1, 2):
-            raise NotImplementedError("depth 3 of the reference is internally inconsistent (SURVEY.md Q12f); use 1 or 2")
+        # the reference tests `depth > 1` (greedy_policy.py:103) and `depth == 3` (:160); its depth-3 branch only
+        # re-assigns the choice depth 2 has just made (:198 after :157), edits a local list and breaks out of its own
+        # loop, so every depth >= 2 returns what depth 2 returns (recorded: tests/golden/greedy_depth3.npz)
+        if not isinstance(depth, (int, np.integer)) or isinstance(depth, bool):
+            raise TypeError("depth must be an int (the reference compares it with 1 and 3)")
         self.board = None
-        self.depth = depth
+        self.depth = int(depth)
         self.device = torch.device(device)
         self.rng = np.random.default_rng()              # kept for attribute parity (unused, as in the reference)
         self.prev_actions = {i: [] for i in range(2)}   # greedy_policy.py:19
@@ -67,7 +70,7 @@ class GreedyGobbletPolicy:
         o = torch.as_tensor(obs_np.astype(np.int8).reshape(1, 117), device=self.device)
         m = torch.as_tensor((mask_np != 0).astype(np.int8).reshape(1, 54), device=self.device)
         p = torch.tensor([prev], dtype=torch.int16, device=self.device)
-        act, chosen, cand, fb = greedy_actions(o, m, p, depth=self.depth, details=True)
+        act, chosen, cand, fb = greedy_actions(o, m, p, depth=1 if self.depth <= 1 else 2, details=True)
         res = torch.stack([act.long(), chosen.long(), cand, fb.long()]).cpu().numpy()[:, 0]
         if res[3]:
             bits = int(res[2]) & (2**64 - 1)

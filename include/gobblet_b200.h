@@ -182,7 +182,9 @@ GBL_API int gbl_sample_legal(const int8_t *mask, uint64_t seed, uint64_t env_id_
                      const uint64_t *step_dev, int32_t *act, int64_t n, void *stream);
 
 /* GreedyGobbletPolicy(depth).compute_action for n boards, one warp per board
- * (greedy_policy.py:38-221; depth 1 or 2).  prev3 (nullable): int16 [n][3], the agent's last three
+ * (greedy_policy.py:38-221; depth 1, 2 or 3 -- the reference's depth-3 branch, :160-208, only re-assigns the choice
+ * depth 2 has already made, edits a local list and leaves its own loop, so depth 3 runs the depth-2 search:
+ * tests/golden/greedy_depth3.npz records that the reference returns the same).  prev3 (nullable): int16 [n][3], the agent's last three
  * actions, -1 = none (greedy_policy.py:211-214).  Outputs (all nullable except act):
  *   act[i]     final action (Philox pick among the candidates when the fallback fires; -1 if the mask is empty)
  *   chosen[i]  choice before the random fallback, -1 = None

@@ -20,6 +20,7 @@ Fixtures
   render_text.npz     stdout of render_mode="text" / "text_full" along one game (debug views, gobblet.py:299-429).
   greedy.npz          GreedyGobbletPolicy(depth 1 and 2).compute_action on sampled positions with
                       np.random.choice patched to expose (chosen-before-fallback, candidates).
+  greedy_depth3.npz   GreedyGobbletPolicy(depth=3) on 16 of those positions (equal to the depth-2 rows, as recorded)
 """
 import ast
 import os
@@ -229,6 +230,58 @@ def greedy_cases(Board, gp_mod, n_pos, rng):
     return out
 
 
+def greedy_depth3_cases(gp_mod, cases, n_pos):
+    """GreedyGobbletPolicy(depth=3) on the first `n_pos` depth-2 rows of `cases` (same observation, mask and history).
+    The depth-3 branch (greedy_policy.py:160-208) only re-assigns `chosen_action = action` (already assigned at :157),
+    edits a local list and breaks out of its own inner loop, so its results must equal the depth-2 rows -- the fixture
+    records what the reference actually returns so that this is a recorded fact, not an argument."""
+    import numpy.random as npr
+
+    captured = {}
+    real_choice = npr.choice
+
+    def fake_choice(a, *args, **kw):
+        captured["cand"] = [int(x) for x in a]
+        return a[0]
+
+    rows = [i for i in range(len(cases["depth"])) if cases["depth"][i] == 2]
+    rows = rows[::max(1, len(rows) // n_pos)][:n_pos]     # spread over the set; a depth-3 call costs up to a minute
+    rec = {k: [] for k in ("row", "obs", "mask", "prev3", "chosen", "cand", "fallback", "returned")}
+    for i in rows:
+        obs, mask = cases["obs"][i].reshape(3, 3, 13), cases["mask"][i]
+        agent = int(obs[0, 0, 12])
+        prev = [int(x) for x in cases["prev3"][i] if x >= 0]
+
+        def run(history):
+            pol = gp_mod.GreedyGobbletPolicy(depth=3)
+            pol.prev_actions[agent] = list(history)
+            captured.clear()
+            npr.choice = fake_choice
+            gp_mod.np.random.choice = fake_choice
+            try:
+                act = int(pol.compute_action(obs, mask))
+            finally:
+                npr.choice = real_choice
+                gp_mod.np.random.choice = real_choice
+            return act, captured.get("cand")
+
+        act, cand0 = run(prev)
+        if cand0 is None:                                 # no fallback: the return value IS the choice;
+            chosen = act                                  # force the fallback once to expose the candidates
+            _, cand0 = run([chosen] * 3)
+        else:                                             # fallback fired: empty history tells whether the choice was None
+            act_free, cand_free = run([])
+            chosen = -1 if cand_free is not None else act_free
+        cand = np.zeros(54, np.int8)
+        cand[cand0] = 1
+        rec["row"].append(i); rec["obs"].append(cases["obs"][i]); rec["mask"].append(mask)
+        rec["prev3"].append(cases["prev3"][i]); rec["chosen"].append(chosen); rec["cand"].append(cand)
+        rec["fallback"].append(chosen < 0 or chosen in prev[-3:]); rec["returned"].append(act)
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["prev3"] = out["prev3"].astype(np.int16)
+    return out
+
+
 def render_text_cases(gob):
     """stdout of the reference's text / text_full renderers (gobblet.py:299-429) along one game."""
     import contextlib
@@ -262,7 +315,9 @@ def main():
     np.savez_compressed(os.path.join(OUT, "env_traces.npz"), **raw_env_traces(gob, 60, rng, 0.0))
     np.savez_compressed(os.path.join(OUT, "env_traces_illegal.npz"), **raw_env_traces(gob, 40, rng, 0.2))
     np.savez_compressed(os.path.join(OUT, "env_wrapped.npz"), **wrapped_env_traces(gob, 40, rng, 0.04))
-    np.savez_compressed(os.path.join(OUT, "greedy.npz"), **greedy_cases(Board, gp, 480, rng))
+    cases = greedy_cases(Board, gp, 480, rng)
+    np.savez_compressed(os.path.join(OUT, "greedy.npz"), **cases)
+    np.savez_compressed(os.path.join(OUT, "greedy_depth3.npz"), **greedy_depth3_cases(gp, cases, 16))
     np.savez_compressed(os.path.join(OUT, "render_text.npz"), **render_text_cases(gob))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -189,6 +189,28 @@ def test_greedy_golden_from_reference(gv1, golden):
         assert _np(fb).tolist() == g["fallback"][sel].tolist()
 
 
+def test_greedy_depth3_golden_from_reference(gv1, golden):
+    """depth=3 through the kernel, the policy object and the adapter == what the reference returned at depth=3."""
+    g = golden("greedy_depth3")
+    obs, mask, prev3 = (torch.as_tensor(g[k]) for k in ("obs", "mask", "prev3"))
+    act, chosen, cand, fb = gv1.greedy_actions(obs.cuda(), mask.cuda(), prev3, depth=3, details=True)
+    assert _np(chosen).tolist() == g["chosen"].tolist() and _np(fb).tolist() == g["fallback"].tolist()
+    assert [int(x) & (2**64 - 1) for x in _np(cand)] == [sum(1 << int(a) for a in np.flatnonzero(c)) for c in g["cand"]]
+    import numpy.random as npr
+    real = npr.choice
+    npr.choice = lambda a, *k, **kw: a[0]                       # the fixture was recorded with this stand-in for the fallback draw
+    try:
+        for k in range(len(g["row"])):
+            pol = gv1.GreedyGobbletPolicy(depth=3)
+            agent = int(g["obs"][k].reshape(3, 3, 13)[0, 0, 12])
+            pol.prev_actions[agent] = [int(x) for x in g["prev3"][k] if x >= 0]
+            assert int(pol.compute_action(g["obs"][k].reshape(3, 3, 13), g["mask"][k])) == int(g["returned"][k]), k
+    finally:
+        npr.choice = real
+    with pytest.raises(TypeError):
+        gv1.GreedyGobbletPolicy(depth=None)                     # the reference fails on `None > 1` (greedy_policy.py:103)
+
+
 def test_abi_rejects_bad_arguments(gv1):
     from gobblet_rl_b200 import ops
     v = gv1.vec_env(40)

@@ -92,6 +92,26 @@ def test_greedy_matches_reference(golden):
     assert 0 < n_fb < len(g["depth"])
 
 
+def test_greedy_depth3_matches_reference_and_equals_depth2(golden):
+    """The reference's depth-3 branch (greedy_policy.py:160-208), restated literally in the oracle, against what the
+    reference itself returned at depth=3 -- and, row by row, against its own depth-2 answers: the branch re-assigns
+    the choice depth 2 has made, edits a local list and breaks out of its own loop, nothing else."""
+    g3, g = golden("greedy_depth3"), golden("greedy")
+    assert len(g3["row"]) >= 16
+    for k, i in enumerate(g3["row"]):
+        assert int(g["depth"][i]) == 2 and np.array_equal(g3["obs"][k], g["obs"][i]) and np.array_equal(g3["prev3"][k], g["prev3"][i])
+        chosen, cand, fb = O.greedy(g3["obs"][k], g3["mask"][k], g3["prev3"][k], 3)
+        assert chosen == int(g3["chosen"][k]) and fb == bool(g3["fallback"][k]), k
+        assert cand == np.flatnonzero(g3["cand"][k]).tolist(), k
+        assert (int(g3["chosen"][k]), bool(g3["fallback"][k])) == (int(g["chosen"][i]), bool(g["fallback"][i]))
+        assert np.array_equal(g3["cand"][k], g["cand"][i])
+    v = O.VecOracle(300, "terminate", "off")                   # and on fresh positions: literal depth 3 == depth 2
+    v.rollout_random(7, seed=31, per_step=False)
+    obs, mask, _ = v.observe()
+    for i in range(300):
+        assert O.greedy(obs[i], mask[i], (-1, -1, -1), 3) == O.greedy(obs[i], mask[i], (-1, -1, -1), 2), i
+
+
 def test_philox_known_answers():
     """Random123 kat_vectors for philox4x32-10."""
     assert [hex(x) for x in O.philox4x32_10([0] * 4, [0] * 2)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
