@@ -5,7 +5,7 @@ dev=torch.device('cuda',0); n=1<<20
 logger = gobblet_v1.vec_env(n, device=dev, seed=1)
 log = logger.rollout_random(20, emit=False, log_actions=True)["actions"]
 h_log = torch.zeros(log.shape, dtype=torch.uint8, pin_memory=True); h_log.copy_(log); torch.cuda.synchronize()
-for kw in (dict(chunks=8), dict(), dict(chunks=32), dict(chunks=1)):
+for kw in (dict(), dict(blocking_events=True), dict(host_threads=15), dict(host_threads=15, blocking_events=True), dict(), dict(blocking_events=True), dict(chunks=16), dict(chunks=1)):
     host = gobblet_v1.HostVecEnv(n, device=dev, seed=1, **kw)
     host.reset()
     ts=[]
