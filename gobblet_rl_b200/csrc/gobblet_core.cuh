@@ -266,6 +266,7 @@ __device__ __forceinline__ uint32_t sample_action(uint32_t m0, uint32_t m1, uint
 // Per warp and step: one 3744-byte bulk store + 108 full 128-bit, fully coalesced STG for the mask
 // (234 + 108 STG with -DGBL_BULK_STORE=0 and in the ragged last warp).
 // Protocol: [stage_recycle] | stage_env | __syncwarp | emit_chunk | __syncwarp, repeated; see the comments of each.
+constexpr int PART_BOTH = 0, PART_OBS = 1, PART_MASK = 2;   // which output stream(s) a warp stages and emits
 constexpr int OBS_IMG_BYTES = 32 * 117, MASK_WORDS = 54;
 constexpr int STAGE_BYTES = OBS_IMG_BYTES + 4 * MASK_WORDS + 8;  // 3968, multiple of 16
 constexpr int OBS_VEC = 234, MASK_VEC = 108;                    // uint4 stores per warp
@@ -388,9 +389,9 @@ __device__ __forceinline__ void fence_smem_for_bulk() {    // generic-proxy smem
 // emit_chunk must have READ it) and zero it for the next scatter.  Callers put it right before stage_env, i.e.
 // AFTER the register-only game logic of the next step: the engine reads the 3744 bytes while the warp computes
 // (waiting right behind the mask stores -- the first version -- cost a third of all warp stall samples).
-template <bool kBulk = kBulkStore>
+template <bool kBulk = kBulkStore, int kPart = PART_BOTH>
 __device__ __forceinline__ void stage_recycle(uint8_t *stage, uint32_t lane) {
-    if (!kBulk) return;
+    if (!kBulk || kPart == PART_MASK) return;
     if (lane == 0) bulk_store_wait_read();
     __syncwarp();
     uint4 *img = reinterpret_cast<uint4 *>(stage);
@@ -404,25 +405,30 @@ __device__ __forceinline__ void stage_recycle(uint8_t *stage, uint32_t lane) {
 
 // stage: all 32 lanes of the warp must call (shuffle inside).  stage = this warp's STAGE_BYTES.
 // The caller puts a __syncwarp() between stage_env and emit_chunk and one after emit_chunk.
-template <bool kBulk = kBulkStore>
+// kPart: PART_BOTH, or only the observation / only the mask (two warps share the emission of 32 envs, see rollout_kernel).
+template <bool kBulk = kBulkStore, int kPart = PART_BOTH>
 __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint32_t lane, const Env &e,
                                           uint32_t m0, uint32_t m1) {
-    uint8_t *mine = stage + 117u * lane;
-    scatter_pieces(mine, e.xo, 0);
-    scatter_pieces(mine, e.yo, 1);
-    scatter_pieces(mine, e.xp, 6);
-    scatter_pieces(mine, e.yp, 7);
+    if (kPart != PART_MASK) {
+        uint8_t *mine = stage + 117u * lane;
+        scatter_pieces(mine, e.xo, 0);
+        scatter_pieces(mine, e.yo, 1);
+        scatter_pieces(mine, e.xp, 6);
+        scatter_pieces(mine, e.yp, 7);
 #pragma unroll
-    for (int p = 0; p < 9; ++p) mine[13 * p + 12] = (uint8_t)e.agent;   // plane 12: the viewer is player_2 (gobblet.py:199-206);
-                                                                         // unconditional (the image is zero): no divergent region
-    uint32_t *mbits = reinterpret_cast<uint32_t *>(stage + OBS_IMG_BYTES);
-    const uint32_t v0 = m0 << c.mso, v1 = __funnelshift_l(m0, m1, c.mso), v2 = __funnelshift_l(m1, 0u, c.mso);
-    uint32_t tail = c.mn2 ? v2 : v1;                    // partial word shared with the next lane
-    uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
-    if (lane == 0) prev = 0;
-    mbits[c.mfo] = v0 | prev;
-    store_word_if(mbits + c.mfo + 1, v1, c.mn2);
-    if (kBulk) fence_smem_for_bulk();
+        for (int p = 0; p < 9; ++p) mine[13 * p + 12] = (uint8_t)e.agent;   // plane 12: the viewer is player_2 (gobblet.py:199-206);
+                                                                             // unconditional (the image is zero): no divergent region
+    }
+    if (kPart != PART_OBS) {
+        uint32_t *mbits = reinterpret_cast<uint32_t *>(stage + OBS_IMG_BYTES);
+        const uint32_t v0 = m0 << c.mso, v1 = __funnelshift_l(m0, m1, c.mso), v2 = __funnelshift_l(m1, 0u, c.mso);
+        uint32_t tail = c.mn2 ? v2 : v1;                    // partial word shared with the next lane
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+        if (lane == 0) prev = 0;
+        mbits[c.mfo] = v0 | prev;
+        store_word_if(mbits + c.mfo + 1, v1, c.mn2);
+    }
+    if (kBulk && kPart != PART_MASK) fence_smem_for_bulk();
 }
 
 // copy / expand + store.  obs_chunk / mask_chunk point at the warp's first env; nvalid = envs of this
@@ -432,21 +438,22 @@ __device__ __forceinline__ void stage_env(uint8_t *stage, const LaneCfg &c, uint
 // must have COMPLETED (not merely been read) before the next one is issued -- that is the group before the
 // newest one when ring >= 2, the newest one when ring == 1.
 constexpr uint32_t EMIT_REUSE_RING = 4u, EMIT_REUSE_ALWAYS = 8u;
-template <bool kStreaming, bool kBulk = kBulkStore>
+template <bool kStreaming, bool kBulk = kBulkStore, int kPart = PART_BOTH>
 __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t *obs_chunk,
                                            int8_t *mask_chunk, int nvalid, uint32_t opts = 0u) {
     const uint32_t skip = opts & 3u;
+    constexpr bool kObs = kPart != PART_MASK, kMask = kPart != PART_OBS;
     uint4 *img = reinterpret_cast<uint4 *>(stage);
     const uint16_t *hb = reinterpret_cast<const uint16_t *>(stage + OBS_IMG_BYTES);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid == 32) {
-        if (kBulk) {
+        if (kBulk && kObs) {
             if (lane == 0 && !(skip & 1u)) {
                 if (opts & EMIT_REUSE_ALWAYS) bulk_store_wait_all();
                 else if (opts & EMIT_REUSE_RING) bulk_store_wait_all_but_latest();
                 bulk_store_issue(obs_chunk, stage, OBS_IMG_BYTES);
             }
-        } else {
+        } else if (kObs) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 uint32_t q = lane + 32u * i;
@@ -460,12 +467,12 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint32_t q = lane + 32u * i;
-            if ((i < 3 || q < MASK_VEC) && !(skip & 2u)) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
+            if (kMask && (i < 3 || q < MASK_VEC) && !(skip & 2u)) store16<kStreaming>(mask_chunk + 16u * q, expand16(hb[q]));
         }
         // kBulk: the image stays with the copy engine; stage_recycle() takes it back before the next stage_env
     } else {  // ragged last warp: vector stores while fully inside, bytes at the edge
         const uint32_t ob = 117u * nvalid, mb = 54u * nvalid;
-        for (uint32_t q = lane; q < OBS_VEC; q += 32u) {
+        for (uint32_t q = lane; kObs && q < OBS_VEC; q += 32u) {
             uint4 v = img[q];
             img[q] = zero;
             if (16u * q + 16u <= ob) store16<kStreaming>(obs_chunk + 16u * q, v);
@@ -475,7 +482,7 @@ __device__ __forceinline__ void emit_chunk(uint8_t *stage, uint32_t lane, int8_t
                     obs_chunk[16u * q + j] = (int8_t)(w >> (8u * (j & 3u)));
                 }
         }
-        for (uint32_t q = lane; q < MASK_VEC; q += 32u) {
+        for (uint32_t q = lane; kMask && q < MASK_VEC; q += 32u) {
             uint4 v = expand16(hb[q]);
             if (16u * q + 16u <= mb) store16<kStreaming>(mask_chunk + 16u * q, v);
             else

@@ -186,11 +186,16 @@ struct RolloutParams {
 // kAux:  any of rew_out / term_out / agent_out / action_log / final_*_out is requested (compiled out otherwise)
 // kBulk: the observation image leaves through the copy engine (TMA bulk store); false = 32-lane LDS.128 -> STG.128 copy,
 //        which has no asynchronous completion to wait for (small batches: one warp per scheduler, latency-bound)
-template <bool kFast, bool kStreaming, bool kAux, int kBlock, bool kBulk>
-__global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rollout_kernel(RolloutParams p) {
+// kPart:  PART_BOTH, or one of TWO warps that share the 32 envs of a chunk: both run the (register-only, deterministic)
+//         game logic, one stages and emits the observations (and owns state, statistics and the aux outputs), the
+//         other the masks.  For small batches (fewer warps than schedulers) a lockstep step is one warp's dependent
+//         instruction chain; this takes the other stream's ~100 instructions out of it.
+template <bool kFast, bool kStreaming, bool kAux, int kBlock, bool kBulk, int kPart>
+__device__ __forceinline__ void rollout_body(const RolloutParams &p, const int64_t block) {
     extern __shared__ __align__(16) uint8_t stage_all[];      // (kBlock/32) * STAGE_BYTES, one staging area per warp
+    constexpr bool kOwner = kPart != PART_MASK;               // stores state / statistics / aux outputs
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x, first = g - lane;
+    const int64_t g = block * kBlock + threadIdx.x, first = g - lane;
     uint8_t *const stage = stage_all + warp * STAGE_BYTES;
     const bool valid = g < p.n;
     Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -217,13 +222,13 @@ __global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rol
         const uint32_t initial = kAux && (p.flags & GBL_EMIT_INITIAL) ? 1u : 0u;
         if (initial) {                          // trajectory-buffer layout: slot 0 = the observation before the first step
             if (emit) {
-                stage_recycle<kBulk && kBulkStore>(stage, lane);
-                stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
+                stage_recycle<kBulk && kBulkStore, kPart>(stage, lane);
+                stage_env<kBulk && kBulkStore, kPart>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + first * GBL_OBS_BYTES, p.mask_out + first * GBL_MASK_BYTES, nvalid, opts);
+                emit_chunk<kStreaming, kBulk && kBulkStore, kPart>(stage, lane, p.obs_out + first * GBL_OBS_BYTES, p.mask_out + first * GBL_MASK_BYTES, nvalid, opts);
                 __syncwarp();
             }
-            if (valid && p.agent_out) p.agent_out[g] = (uint8_t)e.agent;
+            if (kOwner && valid && p.agent_out) p.agent_out[g] = (uint8_t)e.agent;
             slot = 1u;
         }
         // byte offsets of this warp's chunk / this lane's element in the current slot, advanced by one slot per step
@@ -261,10 +266,10 @@ __global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rol
             occupancy(e, u, up);
             legal_mask(e.xo, e.yo, u, up, m0, m1);
             if (kAux && p.final_obs_out) {      // the observation a same-step reset is about to replace
-                stage_recycle<kBulk && kBulkStore>(stage, lane);
-                stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
+                stage_recycle<kBulk && kBulkStore, kPart>(stage, lane);
+                stage_env<kBulk && kBulkStore, kPart>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.final_obs_out + (obs_off - fin_obs_shift),
+                emit_chunk<kStreaming, kBulk && kBulkStore, kPart>(stage, lane, p.final_obs_out + (obs_off - fin_obs_shift),
                                        p.final_mask_out + (mask_off - fin_mask_shift), nvalid, opts);
                 __syncwarp();
             }
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rol
                 e.agent = rs ? 0u : e.agent; e.plies = rs ? 0u : e.plies; e.done = rs ? 0u : e.done; e.trunc = rs ? 0u : e.trunc;
                 m0 = rs ? 0xFFFFFFFFu : m0; m1 = rs ? 0x003FFFFFu : m1;
             }
-            if (kAux && valid) {
+            if (kAux && kOwner && valid) {
                 const int64_t oa = aux_off - aux_shift;
                 if (p.rew_out) *reinterpret_cast<char2 *>(p.rew_out + 2 * oa) = make_char2((signed char)r.r1, (signed char)r.r2);
                 if (p.term_out) p.term_out[oa] = r.term;
@@ -282,10 +287,10 @@ __global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rol
                 if (p.action_log) p.action_log[log_off] = r.acted ? (uint8_t)action : (uint8_t)255;
             }
             if (emit) {
-                stage_recycle<kBulk && kBulkStore>(stage, lane);
-                stage_env<kBulk && kBulkStore>(stage, cfg, lane, e, m0, m1);
+                stage_recycle<kBulk && kBulkStore, kPart>(stage, lane);
+                stage_env<kBulk && kBulkStore, kPart>(stage, cfg, lane, e, m0, m1);
                 __syncwarp();
-                emit_chunk<kStreaming, kBulk && kBulkStore>(stage, lane, p.obs_out + obs_off, p.mask_out + mask_off, nvalid, opts);
+                emit_chunk<kStreaming, kBulk && kBulkStore, kPart>(stage, lane, p.obs_out + obs_off, p.mask_out + mask_off, nvalid, opts);
                 __syncwarp();
             }
             log_off += p.n;
@@ -300,15 +305,26 @@ __global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rol
         body(0, std::true_type{});
 #pragma unroll 2
         for (int32_t t = 1; t < p.T; ++t) body(t, std::false_type{});   // two plies per trip: the own/opponent register swap becomes renaming
-        if (valid) p.state[g] = env_pack(e);
+        if (kOwner && valid) p.state[g] = env_pack(e);
         if (kFast) {   // every step but a reset-only first one was a live, legal step: these follow from the step count
             st.steps = live_steps;
             st.sumlen = plies_start + live_steps - e.plies;
             st.p2w = st.episodes - st.p1w;
         }
-        if (kBulk && kBulkStore && lane == 0) bulk_store_wait_read();
+        if (kBulk && kBulkStore && kOwner && lane == 0) bulk_store_wait_read();
     }
-    if (p.stats) flush_stats<kBlock / 32>(st, valid, p.stats);
+    if (kOwner && p.stats) flush_stats<kBlock / 32>(st, valid, p.stats);
+}
+
+// kSplit: blocks come in pairs -- even blocks emit the observations of chunk blockIdx.x / 2, odd blocks its masks
+template <bool kFast, bool kStreaming, bool kAux, int kBlock, bool kBulk, bool kSplit>
+__global__ void __launch_bounds__(kBlock, kBlock == 32 ? 16 : 1024 / kBlock) rollout_kernel(RolloutParams p) {
+    if (kSplit) {
+        if (blockIdx.x & 1u) rollout_body<kFast, kStreaming, kAux, kBlock, kBulk, PART_MASK>(p, (int64_t)(blockIdx.x >> 1));
+        else rollout_body<kFast, kStreaming, kAux, kBlock, kBulk, PART_OBS>(p, (int64_t)(blockIdx.x >> 1));
+    } else {
+        rollout_body<kFast, kStreaming, kAux, kBlock, kBulk, PART_BOTH>(p, (int64_t)blockIdx.x);
+    }
 }
 
 // ---- masked-uniform sampler over int8 masks -----------------------------------------------------
@@ -525,19 +541,21 @@ static int rollout_block_for(int64_t n, uint32_t flags) {
     return 256;
 }
 
-template <bool F, bool S, bool A, int B, bool K>
+template <bool F, bool S, bool A, int B, bool K, bool SP = false>
 static void launch_rollout(const RolloutParams &p, cudaStream_t s) {
-    const unsigned grid = (unsigned)((p.n + B - 1) / B);
+    const unsigned grid = (unsigned)((p.n + B - 1) / B) * (SP ? 2u : 1u);
     const size_t smem = (size_t)(B / 32) * STAGE_BYTES;
-    rollout_kernel<F, S, A, B, K><<<grid, B, smem, s>>>(p);
+    rollout_kernel<F, S, A, B, K, SP><<<grid, B, smem, s>>>(p);
 }
 template <bool F, bool S, bool A>
-static void launch_rollout_b(const RolloutParams &p, int block, bool bulk, cudaStream_t s) {
+static void launch_rollout_b(const RolloutParams &p, int block, bool bulk, bool split, cudaStream_t s) {
     if constexpr (!S) {
         launch_rollout<F, S, A, 256, true>(p, s);                // plain stores: measurement aid, one size
     } else {
         switch (block) {
-            case 32: return bulk ? launch_rollout<F, S, A, 32, true>(p, s) : launch_rollout<F, S, A, 32, false>(p, s);
+            case 32:
+                if (split) return bulk ? launch_rollout<F, S, A, 32, true, true>(p, s) : launch_rollout<F, S, A, 32, false, true>(p, s);
+                return bulk ? launch_rollout<F, S, A, 32, true>(p, s) : launch_rollout<F, S, A, 32, false>(p, s);
             case 64: return bulk ? launch_rollout<F, S, A, 64, true>(p, s) : launch_rollout<F, S, A, 64, false>(p, s);
             case 128: return launch_rollout<F, S, A, 128, true>(p, s);
             default: return launch_rollout<F, S, A, 256, true>(p, s);
@@ -635,11 +653,16 @@ int gbl_rollout_random(void *state, int64_t n, int32_t T, uint64_t seed, uint64_
     // lane copy instead of the copy engine: on request, or by default up to five warps per SM (latency-bound regime:
     // 0.65 vs 0.71 us per lockstep step at 16 Ki envs, equal at 32 Ki; profiles/r2_sweep_small_batch.json)
     const bool bulk = !((flags & GBL_NO_BULK_STORE_HINT) || (!((flags >> GBL_BLOCK_HINT_SHIFT) & 7u) && n <= 148 * 32 * 5));
+    // two warps per chunk (observation warp / mask warp): on request, or by default while the doubled warps still find
+    // a scheduler each (<= 9472 envs: 0.47 vs 0.59 us per lockstep step at 4096 envs, no gain left at 16 Ki), when
+    // something is emitted at all
+    const bool split = block == 32 && obs_out && !(flags & GBL_NO_SPLIT_HINT) &&
+                       ((flags & GBL_SPLIT_HINT) || (!((flags >> GBL_BLOCK_HINT_SHIFT) & 7u) && n <= 148 * 32 * 2));
     const bool aux = rew_out || term_out || agent_out || action_log || final_obs_out || (flags & GBL_EMIT_INITIAL);
 #define GBL_LAUNCH_ROLLOUT(F, S)                                                    \
     do {                                                                            \
-        if (aux) launch_rollout_b<F, S, true>(p, block, bulk, s);                   \
-        else launch_rollout_b<F, S, false>(p, block, bulk, s);                      \
+        if (aux) launch_rollout_b<F, S, true>(p, block, bulk, split, s);            \
+        else launch_rollout_b<F, S, false>(p, block, bulk, split, s);               \
     } while (0)
     if (fast) {
         if (plain) GBL_LAUNCH_ROLLOUT(true, false);

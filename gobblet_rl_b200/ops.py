@@ -21,6 +21,7 @@ SLOT_FROM_ZERO = 0x20
 EMIT_INITIAL = 0x40
 BLOCK_HINT_SHIFT = 12
 NO_BULK_STORE_HINT = 0x8000
+SPLIT_HINT, NO_SPLIT_HINT = 0x10000, 0x20000
 REC_WORDS = 6                      # packed wire format: 6 x u32 = 24 bytes per env (include/gobblet_b200.h)
 ABI_VERSION = 3
 

@@ -121,13 +121,15 @@ class VecEnv:
         self.kernel_launches += 1
 
     def rollout_random(self, T: int, ring: int = 1, emit: bool = True, per_step: bool = False,
-                       log_actions: bool = False, final: bool = False, block_hint: int = 0, no_bulk: bool = False):
+                       log_actions: bool = False, final: bool = False, block_hint: int = 0, no_bulk: bool = False,
+                       split: Optional[bool] = None):
         """T fused lockstep steps with uniform random legal actions (example_basic.py:50-67) in ONE launch.
 
         emit      write the next observation + mask of every step to ring slot (step % ring)
         per_step  also write rew [ring,N,2], terminated [ring,N], agent_id [ring,N]
         final     also write the observation before a same-step reset replaces it (final_obs / final_mask)
         block_hint  threads per block (32/64/128/256, 0 = chosen from N) -- tuning aid
+        split     two warps per 32 envs, one emitting the observations, one the masks (None = chosen from N) -- tuning aid
         Returns a dict of the buffers that were requested; `self.stats` accumulates episode statistics."""
         n, dev, out = self.num_envs, self.device, {}
         obs_out = mask_out = rew_out = term_out = agent_out = log = fobs = fmask = None
@@ -146,6 +148,7 @@ class VecEnv:
             log = torch.zeros((T, n), dtype=torch.uint8, device=dev)
             out["actions"] = log
         hint = ({0: 0, 32: 1, 64: 2, 128: 3, 256: 4}[int(block_hint)] << ops.BLOCK_HINT_SHIFT) | (ops.NO_BULK_STORE_HINT if no_bulk else 0)
+        hint |= 0 if split is None else ops.SPLIT_HINT if split else ops.NO_SPLIT_HINT
         self._launch_rollout(T, obs_out, mask_out, rew_out, term_out, agent_out, log, fobs, fmask, self.flags | hint)
         return out
 

@@ -66,6 +66,9 @@ extern "C" {
                                          trajectory buffer, filled without a separate observe or copy launch */
 #define GBL_NO_BULK_STORE_HINT 0x8000u /* gbl_rollout_random, 32 / 64-thread blocks only: copy the observation image with the lanes
                                          (LDS.128 -> STG.128) instead of the copy engine (tuning aid) */
+#define GBL_SPLIT_HINT 0x10000u       /* gbl_rollout_random, 32-thread blocks only: two warps per 32 envs, one emits the observations,
+                                       * the other the masks (both run the game logic); default for small batches (tuning aid) */
+#define GBL_NO_SPLIT_HINT 0x20000u    /* never split */
 #define GBL_BLOCK_HINT_SHIFT 12       /* gbl_rollout_random: bits 12-14 = threads per block, 0 auto, 1..4 = 32/64/128/256 (tuning aid) */
 #define GBL_MEASURE_SKIP_OBS_STORES 0x100u  /* gbl_rollout_random only: measurement aid, do everything but the obs stores */
 #define GBL_MEASURE_SKIP_MASK_STORES 0x200u /* gbl_rollout_random only: measurement aid, do everything but the mask stores */

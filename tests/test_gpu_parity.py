@@ -488,14 +488,18 @@ def test_rollout_block_sizes_and_short_rings_agree(gv1, n):
     T = 24
     ref = gv1.vec_env(n, seed=6)
     base = ref.rollout_random(T, ring=T, per_step=True, log_actions=True, final=True)
-    for hint, ring, no_bulk in ((32, T, False), (64, T, False), (128, 2, False), (256, 1, False), (0, 3, False), (32, 1, False),
-                                (32, T, True), (64, 2, True), (0, 1, True)):
+    for hint, ring, no_bulk, split in ((32, T, False, False), (64, T, False, None), (128, 2, False, None), (256, 1, False, None),
+                                       (0, 3, False, None), (32, 1, False, False), (32, T, True, False), (64, 2, True, None),
+                                       (0, 1, True, None), (0, T, False, False), (32, T, False, True), (32, 2, True, True),
+                                       (32, 1, False, True), (0, 3, True, True)):
+        # split: two warps per 32 envs (observation warp / mask warp); None = the library's choice for this N
         v = gv1.vec_env(n, seed=6)
-        out = v.rollout_random(T, ring=ring, per_step=True, log_actions=True, final=True, block_hint=hint, no_bulk=no_bulk)
+        out = v.rollout_random(T, ring=ring, per_step=True, log_actions=True, final=True, block_hint=hint, no_bulk=no_bulk,
+                               split=split)
         assert torch.equal(out["actions"], base["actions"]) and torch.equal(v.state, ref.state) and torch.equal(v.stats, ref.stats)
         for s in range(max(0, T - ring), T):
             for key in ("obs", "mask", "final_obs", "final_mask", "rew", "terminated", "agent_id"):
-                assert torch.equal(out[key][s % ring], base[key][s]), (hint, ring, s, key)
+                assert torch.equal(out[key][s % ring], base[key][s]), (hint, ring, no_bulk, split, s, key)
 
 
 def test_skip255_only_skips_exactly_255(gv1):
