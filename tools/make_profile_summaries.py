@@ -73,8 +73,9 @@ def main():
     for name, csvname, jname, per, nunits, how in (
             ("greedy", "r2_greedy_depth2_ncu_full.csv", "greedy_issue.json", "warp_instructions_per_board", 65536,
              "-k regex:greedy_kernel -s 1 -c 1 python tools/greedy_case.py --iters 1"),
-            ("small", "r2_small_batch_kernel_ncu_full.csv", "small_batch_issue.json", "warp_instructions_per_warp_step", 128 * 512,
-             "-k regex:rollout_kernel -s 4 -c 1 python tools/small_batch_case.py  (4096 envs x 512 fused steps)"),
+            ("small", "r2_small_batch_kernel_ncu_full.csv", "small_batch_issue.json", "warp_instructions_per_32env_step_both_warps", 128 * 512,
+             "-k regex:rollout_kernel -s 4 -c 1 python tools/small_batch_case.py  (4096 envs x 512 fused steps; two warps per 32 envs: "
+             "observation warp + mask warp)"),
             ("collect", "r2_collect_kernel_ncu_full.csv", "collect_issue.json", "warp_instructions_per_warp_slot", 4096 * 17,
              "-k regex:rollout_kernel -s 3 -c 1 python tools/collect_case.py --iters 1  (131 072 envs x (1 + 16) emitted slots)")):
         rep = f"{g}/{tag}_{name}.ncu-rep"
@@ -95,7 +96,7 @@ def main():
     # ---- SASS excerpt of the timed instance
     so = os.path.join(REPO, "gobblet_rl_b200", "csrc", "libgobblet_b200.so")
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-    fn = "_ZN3gbl14rollout_kernelILb1ELb1ELb0ELi256ELb1EEEvNS_13RolloutParamsE"
+    fn = "_ZN3gbl14rollout_kernelILb1ELb1ELb0ELi256ELb1ELb0EEEvNS_13RolloutParamsE"
     body = sass.split("Function : " + fn)[1].split("Function : ")[0].splitlines()
     ins = [ln for ln in body if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
     keep = re.compile(r"STS\.U8|STS\.128|FENCE|UBLKCP|UTMACMDFLUSH|DEPBAR|STG\.E|LDG|WARPSYNC|HMMA|UTCMMA|SHFL")
