@@ -449,6 +449,20 @@ def measure_configs(a, ctx):
         dt = device_time(lambda: small.rollout_random(T2, ring=4, block_hint=hint), 3, warmup=1)
         per_block["auto" if hint == 0 else str(hint)] = dt / T2 * 1e6
     best = min(per_block.values())
+    # gate: the timed instance (chosen from N: two warps per 32 envs, no aux outputs) == the 256-thread instance on the
+    # device, and its logged twin == the CPU oracle, 4096 envs x 48 steps
+    ga, gb, gc = (gobblet_v1.vec_env(n2, device=dev, seed=5) for _ in range(3))
+    oa = ga.rollout_random(48, ring=48)
+    ob = gb.rollout_random(48, ring=48, block_hint=256)
+    oc = gc.rollout_random(48, ring=48, per_step=True, log_actions=True)
+    assert torch.equal(oa["obs"], ob["obs"]) and torch.equal(oa["mask"], ob["mask"]) and torch.equal(ga.state, gb.state), "c2 gate"
+    assert torch.equal(oa["obs"], oc["obs"]) and torch.equal(oa["mask"], oc["mask"]) and torch.equal(ga.stats, gc.stats), "c2 gate"
+    ora = O.VecOracle(n2)
+    want = ora.rollout_random(48, seed=5)
+    for key in ("actions", "obs", "mask", "rew", "terminated", "agent_id"):
+        assert np.array_equal(oc[key].cpu().numpy(), want[key]), f"c2 gate: {key} differs from the oracle"
+    assert gc.stats.tolist() == ora.stats.tolist(), "c2 gate: statistics differ from the oracle"
+    del ga, gb, gc, oa, ob, oc
     gsmall = gobblet_v1.vec_env(n2, device=dev, seed=0, graph_safe=True)
 
     def per_step_launches():
@@ -468,7 +482,9 @@ def measure_configs(a, ctx):
                  "us_per_lockstep_step_by_block_threads": per_block, "best_us": best,
                  "us_per_lockstep_step_cuda_graph_of_1step_launches": dt_graph * 1e6,
                  "hbm_time_us": n2 * BYTES_PER_ENV_STEP / (peak * 1e9) * 1e6,
-                 "note": "one fused launch of 4096 steps; latency-bound (a dependent chain per warp), the HBM time is shown for scale"}
+                 "gate": "4096 envs x 48 steps: timed instance == 256-thread instance == logged instance (device), logged instance == oracle",
+                 "note": "one fused launch of 4096 steps; latency-bound (a dependent chain per warp; two warps per 32 envs share "
+                         "the emission: observation warp / mask warp), the HBM time is shown for scale"}
 
     # ---- c4: greedy depth 2 on 65 536 boards (warp per board; issue-bound) ------------------------------------------
     src = gobblet_v1.vec_env(1 << 18, device=dev, seed=7, autoreset="off")
